@@ -1,0 +1,808 @@
+// d3d_api.cu -- C ABI of libdeconv3d_b200.so (see include/deconv3d_b200.h).
+//
+// Host-side runtime of the likelihood hot path: device memory, layout
+// conversion, kernel selection and launch, segmentation of the sweep at the
+// residual-refresh points of lib/run.py:525-534, CUDA-event timing.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+#include <string>
+#include <algorithm>
+
+#include "../../include/deconv3d_b200.h"
+#include "d3d_kernels.cuh"
+
+using namespace d3d;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return fail(e__ == cudaErrorMemoryAllocation ? D3D_ENOMEM : D3D_ECUDA,      \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),        \
+                        __FILE__, __LINE__);                                            \
+    } while (0)
+
+struct d3d_ctx {
+    int device = 0;
+    int dtype = D3D_F64;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    Problem pb;
+    bool have_problem = false, have_tables = false, have_params = false;
+    std::vector<void*> allocs;          // problem-lifetime allocations
+    void* rt_x = nullptr; void* rt_yu = nullptr; void* rt_nc = nullptr;
+    double* d_lines = nullptr;          // [n_chains][H][W][Dp] scratch of the forward model
+    int threads = 256, ne = 0;          // sweep launch configuration
+    size_t sweep_smem = 0;
+    int64_t launches = 0, last_bytes = 0, last_updates = 0;
+    int64_t window_voxels_per_sweep = 0;   // sum over cubes of sum_sites wh*ww*D * chains_per_cube
+    std::vector<int> h_nsites;
+    size_t elem() const { return dtype == D3D_F64 ? 8 : 4; }
+};
+
+template <typename P>
+static int dalloc(d3d_ctx* c, P** p, size_t bytes) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+        return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    c->allocs.push_back(q);
+    *p = (P*)q;
+    return 0;
+}
+
+static void free_problem(d3d_ctx* c) {
+    for (void* p : c->allocs) cudaFree(p);
+    c->allocs.clear();
+    c->d_lines = nullptr;
+    c->have_problem = false;
+    c->have_params = false;
+}
+
+extern "C" int d3d_abi_version(void) { return D3D_ABI_VERSION; }
+extern "C" const char* d3d_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int d3d_ctx_create(d3d_ctx** out, int device, int dtype) {
+    if (!out) return fail(D3D_EINVAL, "d3d_ctx_create: out is NULL");
+    if (dtype != D3D_F32 && dtype != D3D_F64)
+        return fail(D3D_EINVAL, "d3d_ctx_create: dtype must be D3D_F32 or D3D_F64");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(D3D_ECUDA, "no CUDA device available (%s); deconv3d_b200 has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(D3D_EINVAL, "device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    d3d_ctx* c = new d3d_ctx();
+    c->device = device;
+    c->dtype = dtype;
+    memset(&c->pb, 0, sizeof(Problem));
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_problem(c);
+    if (c->rt_x) cudaFree(c->rt_x);
+    if (c->rt_yu) cudaFree(c->rt_yu);
+    if (c->rt_nc) cudaFree(c->rt_nc);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int d3d_ctx_set_stream(d3d_ctx* c, void* s) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+extern "C" int d3d_ctx_synchronize(d3d_ctx* c) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+template <typename T>
+static int ingest(d3d_ctx* c, const double* src_any, const double* nan_src_dev, void* dst, int n,
+                  int mode, double** staged_out) {
+    const Problem& pb = c->pb;
+    size_t cnt = (size_t)n * pb.D * pb.H * pb.W;
+    double* stage = nullptr;
+    CK(cudaMalloc(&stage, cnt * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(stage, src_any, cnt * sizeof(double), cudaMemcpyDefault, c->stream);
+    if (e != cudaSuccess) { cudaFree(stage); return fail(D3D_ECUDA, "copy of cube failed: %s", cudaGetErrorString(e)); }
+    long long blocks = (long long)n * pb.H * ((pb.Dp + 31) / 32) * ((pb.W + 31) / 32);
+    ingest_kernel<T><<<(unsigned)blocks, 256, 0, c->stream>>>(stage, nan_src_dev, (T*)dst, n, pb.D,
+                                                              pb.Dp, pb.H, pb.W, mode);
+    c->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(stage); return fail(D3D_ECUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
+    if (staged_out) { *staged_out = stage; return 0; }
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(stage);
+    return 0;
+}
+
+static void choose_launch(d3d_ctx* c) {
+    const Problem& pb = c->pb;
+    const int vec = c->dtype == D3D_F64 ? 2 : 4;
+    const int zl = pb.Dp / vec;
+    const int npos = pb.fh * pb.fw;
+    int best_threads = 256, best_ne = 0;
+    for (int threads = 256; threads <= 512; threads *= 2) {
+        int t = std::max(threads, ((std::max(pb.Dp, zl) + 31) / 32) * 32);
+        if (t > 1024) break;
+        int nc = std::max(1, t / zl);
+        int need = (npos + nc - 1) / nc;
+        if (need <= 16) { best_threads = t; best_ne = need <= 4 ? 4 : need <= 8 ? 8 : 16; break; }
+        best_threads = std::max(256, ((std::max(pb.Dp, zl) + 31) / 32) * 32);
+    }
+    c->threads = best_threads;
+    c->ne = best_ne;
+    c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
+}
+
+extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int D, int H, int W,
+                               const double* data, const double* var, int var_kind,
+                               const uint8_t* mask, const double* fsf, int fh, int fw,
+                               const double* lsf, const double* pmin, const double* pmax,
+                               const double* jump_amp, const double* gibbs_prior_var) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    if (n_cubes < 1 || chains_per_cube < 1 || D < 1 || H < 1 || W < 1)
+        return fail(D3D_EINVAL, "d3d_set_problem: sizes must be positive");
+    if (D > 1024) return fail(D3D_EINVAL, "d3d_set_problem: at most 1024 channels are supported");
+    if (fh < 1 || fw < 1 || fh % 2 == 0 || fw % 2 == 0)
+        return fail(D3D_EINVAL, "FSF *must* be of odd dimensions");              // lib/run.py:210-211
+    if (!data || !var || !fsf || !pmin || !pmax || !jump_amp || !gibbs_prior_var)
+        return fail(D3D_EINVAL, "d3d_set_problem: NULL argument");
+    if (var_kind != D3D_VAR_SCALAR && var_kind != D3D_VAR_CUBE)
+        return fail(D3D_EINVAL, "d3d_set_problem: bad var_kind");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_problem(c);
+    Problem& pb = c->pb;
+    RtTables keep_rt = pb.rt;
+    unsigned long long keep_seed = pb.seed;
+    unsigned int keep_first = pb.first_chain;
+    memset(&pb, 0, sizeof pb);
+    pb.rt = keep_rt; pb.seed = keep_seed; pb.first_chain = keep_first;
+    const int vec = c->dtype == D3D_F64 ? 2 : 4;
+    pb.D = D; pb.H = H; pb.W = W; pb.Dp = ((D + vec - 1) / vec) * vec;
+    pb.fh = fh; pb.fw = fw; pb.fhh = (fh - 1) / 2; pb.fhw = (fw - 1) / 2;
+    pb.n_cubes = n_cubes; pb.chains_per_cube = chains_per_cube;
+    pb.n_chains = n_cubes * chains_per_cube;
+    pb.var_is_cube = var_kind == D3D_VAR_CUBE;
+    pb.has_lsf = lsf != nullptr;
+    // padded spectral length of lib/convolution.py:141-144: 2**len(binary_repr(D-1))
+    { int bits = 1; unsigned v = (unsigned)(D - 1); while (v >>= 1) ++bits; pb.P = 1 << bits; }
+
+    const size_t HW = (size_t)H * W, cube_elems = HW * pb.Dp;
+    int rc;
+    void* d_data; void* d_iv = nullptr; void* d_err;
+    if ((rc = dalloc(c, &d_data, (size_t)n_cubes * cube_elems * c->elem()))) return rc;
+    if ((rc = dalloc(c, &d_err, (size_t)pb.n_chains * cube_elems * c->elem()))) return rc;
+    CK(cudaMemsetAsync(d_err, 0, (size_t)pb.n_chains * cube_elems * c->elem(), c->stream));
+    double* staged_data = nullptr;
+    if (c->dtype == D3D_F64) rc = ingest<double>(c, data, nullptr, d_data, n_cubes, 0, &staged_data);
+    else rc = ingest<float>(c, data, nullptr, d_data, n_cubes, 0, &staged_data);
+    if (rc) return rc;
+    double* d_ivs = nullptr;
+    if (pb.var_is_cube) {
+        if ((rc = dalloc(c, &d_iv, (size_t)n_cubes * cube_elems * c->elem()))) { cudaFree(staged_data); return rc; }
+        if (c->dtype == D3D_F64) rc = ingest<double>(c, var, staged_data, d_iv, n_cubes, 1, nullptr);
+        else rc = ingest<float>(c, var, staged_data, d_iv, n_cubes, 1, nullptr);
+        if (rc) { cudaFree(staged_data); return rc; }
+    } else {
+        std::vector<double> hv(n_cubes);
+        CK(cudaMemcpy(hv.data(), var, n_cubes * sizeof(double), cudaMemcpyDefault));
+        for (auto& v : hv) v = 1.0 / v;
+        if ((rc = dalloc(c, &d_ivs, n_cubes * sizeof(double)))) { cudaFree(staged_data); return rc; }
+        CK(cudaMemcpy(d_ivs, hv.data(), n_cubes * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(staged_data);
+    pb.data = d_data; pb.iv = d_iv; pb.iv_scalar = d_ivs; pb.err = d_err;
+
+    // mask -> row-major site lists (lib/run.py:553-566)
+    std::vector<uint8_t> hmask((size_t)n_cubes * HW, 1);
+    if (mask) CK(cudaMemcpy(hmask.data(), mask, hmask.size(), cudaMemcpyDefault));
+    std::vector<int> nsites(n_cubes, 0);
+    int max_sites = 1;
+    for (int q = 0; q < n_cubes; ++q) {
+        int cnt = 0;
+        for (size_t i = 0; i < HW; ++i) cnt += hmask[q * HW + i] == 1;
+        nsites[q] = cnt;
+        max_sites = std::max(max_sites, cnt);
+    }
+    std::vector<int> sites((size_t)n_cubes * max_sites, 0);
+    int64_t wvox = 0;
+    for (int q = 0; q < n_cubes; ++q) {
+        int k = 0;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x)
+                if (hmask[q * HW + (size_t)y * W + x] == 1) {
+                    sites[(size_t)q * max_sites + k++] = y * W + x;
+                    int wh = std::min(y + pb.fhh + 1, H) - std::max(y - pb.fhh, 0);
+                    int ww = std::min(x + pb.fhw + 1, W) - std::max(x - pb.fhw, 0);
+                    wvox += (int64_t)wh * ww * D * chains_per_cube;
+                }
+    }
+    c->window_voxels_per_sweep = wvox;
+    c->h_nsites = nsites;
+    pb.max_sites = max_sites;
+    uint8_t* d_mask; int* d_sites; int* d_ns;
+    if ((rc = dalloc(c, &d_mask, hmask.size()))) return rc;
+    if ((rc = dalloc(c, &d_sites, sites.size() * sizeof(int)))) return rc;
+    if ((rc = dalloc(c, &d_ns, n_cubes * sizeof(int)))) return rc;
+    CK(cudaMemcpy(d_mask, hmask.data(), hmask.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sites, sites.data(), sites.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ns, nsites.data(), n_cubes * sizeof(int), cudaMemcpyHostToDevice));
+    pb.mask = d_mask; pb.sites = d_sites; pb.n_sites = d_ns;
+
+    // FSF and the circular LSF kernel.  lib/convolution.py:89-160 in direct form
+    // (SURVEY.md 8a-3): out[j] = sum_i line[i]*lsf[t], t = ((j-i+P/2) mod P) - half,
+    // kept iff 0 <= t < D  =>  K[m] = lsf[((m+P/2) mod P) - half], m = (j-i) mod P.
+    std::vector<double> hfsf((size_t)fh * fw), hk(pb.P, 0.0);
+    CK(cudaMemcpy(hfsf.data(), fsf, hfsf.size() * sizeof(double), cudaMemcpyDefault));
+    if (lsf) {
+        std::vector<double> hl(D);
+        CK(cudaMemcpy(hl.data(), lsf, D * sizeof(double), cudaMemcpyDefault));
+        int diff = pb.P - D, half = (diff & 1) ? diff / 2 + 1 : diff / 2;
+        for (int m = 0; m < pb.P; ++m) {
+            int t = ((m + pb.P / 2) % pb.P) - half;
+            hk[m] = (t >= 0 && t < D) ? hl[t] : 0.0;
+        }
+    } else {
+        hk[0] = 1.0;
+    }
+    double* d_fsf; double* d_k;
+    if ((rc = dalloc(c, &d_fsf, hfsf.size() * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_k, hk.size() * sizeof(double)))) return rc;
+    CK(cudaMemcpy(d_fsf, hfsf.data(), hfsf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_k, hk.data(), hk.size() * sizeof(double), cudaMemcpyHostToDevice));
+    pb.fsf = d_fsf; pb.kcirc = d_k;
+
+    double *d_pmin, *d_pmax, *d_prior;
+    if ((rc = dalloc(c, &d_pmin, n_cubes * 3 * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_pmax, n_cubes * 3 * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_prior, n_cubes * sizeof(double)))) return rc;
+    CK(cudaMemcpy(d_pmin, pmin, n_cubes * 3 * sizeof(double), cudaMemcpyDefault));
+    CK(cudaMemcpy(d_pmax, pmax, n_cubes * 3 * sizeof(double), cudaMemcpyDefault));
+    CK(cudaMemcpy(d_prior, gibbs_prior_var, n_cubes * sizeof(double), cudaMemcpyDefault));
+    pb.pmin = d_pmin; pb.pmax = d_pmax; pb.prior_var = d_prior;
+    CK(cudaMemcpy(pb.jump, jump_amp, 3 * sizeof(double), cudaMemcpyDefault));
+
+    double* d_params; long long* d_acc; long long* d_it; double* d_rate; int* d_active; int* d_status;
+    if ((rc = dalloc(c, &d_params, (size_t)pb.n_chains * HW * 3 * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_acc, pb.n_chains * sizeof(long long)))) return rc;
+    if ((rc = dalloc(c, &d_it, pb.n_chains * sizeof(long long)))) return rc;
+    if ((rc = dalloc(c, &d_rate, pb.n_chains * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_active, pb.n_chains * sizeof(int)))) return rc;
+    if ((rc = dalloc(c, &d_status, sizeof(int)))) return rc;
+    CK(cudaMemset(d_params, 0, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
+    CK(cudaMemset(d_status, 0, sizeof(int)));
+    pb.params = d_params; pb.accepted = d_acc; pb.iters = d_it; pb.rate = d_rate;
+    pb.active = d_active; pb.status = d_status;
+    if ((rc = dalloc(c, &c->d_lines, (size_t)pb.n_chains * cube_elems * sizeof(double)))) return rc;
+
+    choose_launch(c);
+    c->have_problem = true;
+    return 0;
+}
+
+static int reset_chain_control(d3d_ctx* c) {
+    const Problem& pb = c->pb;
+    std::vector<long long> acc(pb.n_chains), it(pb.n_chains, 1);
+    std::vector<double> rate(pb.n_chains, 0.0);
+    std::vector<int> act(pb.n_chains, 1);
+    for (int k = 0; k < pb.n_chains; ++k) acc[k] = c->h_nsites[k / pb.chains_per_cube];  // :341
+    CK(cudaMemcpyAsync(pb.accepted, acc.data(), acc.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(pb.iters, it.data(), it.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(pb.rate, rate.data(), rate.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(pb.active, act.data(), act.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int d3d_set_rtnorm_tables(d3d_ctx* c, const double* x, int nx, const double* yu, int nyu,
+                                     const int32_t* ncell, int nncell) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    if (nx != 4002 || nyu != 4001 || nncell != 8961 || !x || !yu || !ncell)
+        return fail(D3D_EINVAL, "rtnorm tables must have 4002/4001/8961 entries (lib/rtnorm.py:227-2681)");
+    CK(cudaSetDevice(c->device));
+    if (!c->rt_x) {
+        CK(cudaMalloc(&c->rt_x, nx * sizeof(double)));
+        CK(cudaMalloc(&c->rt_yu, nyu * sizeof(double)));
+        CK(cudaMalloc(&c->rt_nc, nncell * sizeof(int)));
+    }
+    CK(cudaMemcpy(c->rt_x, x, nx * sizeof(double), cudaMemcpyDefault));
+    CK(cudaMemcpy(c->rt_yu, yu, nyu * sizeof(double), cudaMemcpyDefault));
+    CK(cudaMemcpy(c->rt_nc, ncell, nncell * sizeof(int), cudaMemcpyDefault));
+    c->pb.rt.x = (const double*)c->rt_x;
+    c->pb.rt.yu = (const double*)c->rt_yu;
+    c->pb.rt.ncell = (const int*)c->rt_nc;
+    c->have_tables = true;
+    return 0;
+}
+
+extern "C" int d3d_set_rng(d3d_ctx* c, uint64_t seed, uint32_t first_chain_id) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    c->pb.seed = seed;
+    c->pb.first_chain = first_chain_id;
+    return 0;
+}
+
+extern "C" int d3d_set_params(d3d_ctx* c, const double* params) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_set_params before d3d_set_problem");
+    if (!params) return fail(D3D_EINVAL, "params is NULL");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    CK(cudaMemcpyAsync(pb.params, params, (size_t)pb.n_chains * pb.H * pb.W * 3 * sizeof(double),
+                       cudaMemcpyDefault, c->stream));
+    c->have_params = true;
+    return reset_chain_control(c);
+}
+
+extern "C" int d3d_get_params(d3d_ctx* c, double* params) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_get_params before d3d_set_problem");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    CK(cudaMemcpyAsync(params, pb.params, (size_t)pb.n_chains * pb.H * pb.W * 3 * sizeof(double),
+                       cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int d3d_init_params_uniform(d3d_ctx* c) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_init_params_uniform before d3d_set_problem");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    size_t n = (size_t)pb.n_chains * pb.H * pb.W;
+    init_params_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(pb);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->have_params = true;
+    return reset_chain_control(c);
+}
+
+// ------------------------------------------------------------------------------
+// forward model
+static int stencil_config(const d3d_ctx* c, int* TY, int* TX, int* ZC, size_t* smem) {
+    const Problem& pb = c->pb;
+    const size_t limit = 200 * 1024;
+    int ty = 8, tx = 8;
+    while (ty > pb.H && ty > 1) ty /= 2;
+    while (tx > pb.W && tx > 1) tx /= 2;
+    for (;;) {
+        size_t per_ch = (size_t)(ty + pb.fh - 1) * (tx + pb.fw - 1) * sizeof(double);
+        size_t fixed = (size_t)pb.fh * pb.fw * sizeof(double);
+        long long zc = ((long long)limit - (long long)fixed) / (long long)per_ch;
+        if (zc >= 1) {
+            int z = (int)std::min<long long>(zc, pb.Dp);
+            *TY = ty; *TX = tx; *ZC = z; *smem = fixed + per_ch * z;
+            return 0;
+        }
+        if (ty == 1 && tx == 1) return fail(D3D_EINVAL, "FSF too large for the stencil kernel");
+        if (ty >= tx && ty > 1) ty /= 2; else if (tx > 1) tx /= 2; else ty /= 2;
+    }
+}
+
+
+static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double* sim_dev,
+                       int write_err, double* chi2_dev) {
+    const Problem& pb = c->pb;
+    const size_t HW = (size_t)pb.H * pb.W;
+    {
+        const int threads = 256, wpb = threads / 32;
+        size_t total = (size_t)pb.n_chains * HW;
+        unsigned blocks = (unsigned)std::min<size_t>((total + wpb - 1) / wpb, 148 * 16);
+        size_t smem = ((size_t)pb.P + (size_t)wpb * pb.Dp) * sizeof(double);
+        lines_kernel<<<blocks, threads, smem, c->stream>>>(pb, d_params, c->d_lines, convolve);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
+    int TY, TX, ZC; size_t smem;
+    int rc = stencil_config(c, &TY, &TX, &ZC, &smem);
+    if (rc) return rc;
+    dim3 grid((unsigned)(pb.n_chains * ((pb.H + TY - 1) / TY) * ((pb.W + TX - 1) / TX)),
+              (unsigned)((pb.Dp + ZC - 1) / ZC));
+    if (c->dtype == D3D_F64) {
+        CK(cudaFuncSetAttribute(stencil_zchunk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stencil_zchunk_kernel<double><<<grid, 256, smem, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev, TY, TX, ZC);
+    } else {
+        CK(cudaFuncSetAttribute(stencil_zchunk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stencil_zchunk_kernel<float><<<grid, 256, smem, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev, TY, TX, ZC);
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int forward_common(d3d_ctx* c, const double* params_any, int convolve, double* sim_out,
+                          int write_err, double* chi2_out) {
+    const Problem& pb = c->pb;
+    CK(cudaSetDevice(c->device));
+    const size_t HW = (size_t)pb.H * pb.W;
+    const size_t sim_cnt = (size_t)pb.n_chains * pb.D * HW;
+    double* d_params = pb.params;
+    double* tmp_params = nullptr;
+    if (params_any) {
+        CK(cudaMalloc(&tmp_params, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
+        cudaError_t e = cudaMemcpyAsync(tmp_params, params_any, (size_t)pb.n_chains * HW * 3 * sizeof(double), cudaMemcpyDefault, c->stream);
+        if (e != cudaSuccess) { cudaFree(tmp_params); return fail(D3D_ECUDA, "params copy failed: %s", cudaGetErrorString(e)); }
+        d_params = tmp_params;
+    }
+    double* d_sim = nullptr; double* d_chi = nullptr;
+    int rc = 0;
+    if (sim_out) { cudaError_t e = cudaMalloc(&d_sim, sim_cnt * sizeof(double)); if (e != cudaSuccess) rc = fail(D3D_ENOMEM, "cudaMalloc sim failed"); }
+    if (!rc && chi2_out) {
+        cudaError_t e = cudaMalloc(&d_chi, pb.n_chains * sizeof(double));
+        if (e != cudaSuccess) rc = fail(D3D_ENOMEM, "cudaMalloc chi2 failed");
+        else cudaMemsetAsync(d_chi, 0, pb.n_chains * sizeof(double), c->stream);
+    }
+    if (!rc) rc = run_forward(c, d_params, convolve, d_sim, write_err, d_chi);
+    if (!rc && sim_out) {
+        cudaError_t e = cudaMemcpyAsync(sim_out, d_sim, sim_cnt * sizeof(double), cudaMemcpyDefault, c->stream);
+        if (e != cudaSuccess) rc = fail(D3D_ECUDA, "sim copy failed: %s", cudaGetErrorString(e));
+    }
+    if (!rc && chi2_out) {
+        cudaError_t e = cudaMemcpyAsync(chi2_out, d_chi, pb.n_chains * sizeof(double), cudaMemcpyDefault, c->stream);
+        if (e != cudaSuccess) rc = fail(D3D_ECUDA, "chi2 copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (!rc && e != cudaSuccess) rc = fail(D3D_ECUDA, "forward failed: %s", cudaGetErrorString(e));
+    if (tmp_params) cudaFree(tmp_params);
+    if (d_sim) cudaFree(d_sim);
+    if (d_chi) cudaFree(d_chi);
+    return rc;
+}
+
+extern "C" int d3d_forward(d3d_ctx* c, double* sim_out, int write_err, double* chi2_out) {
+    if (!c || !c->have_problem || !c->have_params)
+        return fail(D3D_ESTATE, "d3d_forward needs d3d_set_problem and parameters");
+    return forward_common(c, nullptr, 1, sim_out, write_err, chi2_out);
+}
+
+extern "C" int d3d_simulate(d3d_ctx* c, const double* params, double* sim_out) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_simulate before d3d_set_problem");
+    if (!params || !sim_out) return fail(D3D_EINVAL, "NULL argument");
+    return forward_common(c, params, 1, sim_out, 0, nullptr);
+}
+
+
+extern "C" int d3d_simulate_clean(d3d_ctx* c, const double* params, double* sim_out) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_simulate_clean before d3d_set_problem");
+    if (!params || !sim_out) return fail(D3D_EINVAL, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    const size_t HW = (size_t)pb.H * pb.W;
+    size_t total = (size_t)pb.n_chains * pb.D * HW;
+    double *d_p = nullptr, *d_o = nullptr;
+    CK(cudaMalloc(&d_p, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_o, total * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(d_p); return fail(D3D_ENOMEM, "cudaMalloc failed"); }
+    cudaMemcpyAsync(d_p, params, (size_t)pb.n_chains * HW * 3 * sizeof(double), cudaMemcpyDefault, c->stream);
+    clean_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(pb, d_p, d_o);
+    c->launches++;
+    cudaMemcpyAsync(sim_out, d_o, total * sizeof(double), cudaMemcpyDefault, c->stream);
+    e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_p); cudaFree(d_o);
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "simulate_clean failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int d3d_get_residual(d3d_ctx* c, double* err_out) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_get_residual before d3d_set_problem");
+    if (!err_out) return fail(D3D_EINVAL, "NULL argument");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    size_t total = (size_t)pb.n_chains * pb.D * pb.H * pb.W;
+    double* d_o = nullptr;
+    CK(cudaMalloc(&d_o, total * sizeof(double)));
+    long long blocks = (long long)pb.n_chains * pb.H * ((pb.Dp + 31) / 32) * ((pb.W + 31) / 32);
+    if (c->dtype == D3D_F64)
+        egest_kernel<double><<<(unsigned)blocks, 256, 0, c->stream>>>((const double*)pb.err, d_o, pb.n_chains, pb.D, pb.Dp, pb.H, pb.W);
+    else
+        egest_kernel<float><<<(unsigned)blocks, 256, 0, c->stream>>>((const float*)pb.err, d_o, pb.n_chains, pb.D, pb.Dp, pb.H, pb.W);
+    c->launches++;
+    cudaMemcpyAsync(err_out, d_o, total * sizeof(double), cudaMemcpyDefault, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_o);
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "get_residual failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int d3d_conv1d(d3d_ctx* c, const double* lines, int n, int batch, const double* lsf,
+                          double* out) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    if (!lines || !lsf || !out || n < 1 || batch < 1) return fail(D3D_EINVAL, "d3d_conv1d: bad argument");
+    CK(cudaSetDevice(c->device));
+    int bits = 1; { unsigned v = (unsigned)(n - 1); while (v >>= 1) ++bits; }
+    const int P = 1 << bits;
+    std::vector<double> hl(n), hk(P, 0.0);
+    CK(cudaMemcpy(hl.data(), lsf, n * sizeof(double), cudaMemcpyDefault));
+    int diff = P - n, half = (diff & 1) ? diff / 2 + 1 : diff / 2;
+    for (int m = 0; m < P; ++m) {
+        int t = ((m + P / 2) % P) - half;
+        hk[m] = (t >= 0 && t < n) ? hl[t] : 0.0;
+    }
+    double *d_l = nullptr, *d_k = nullptr, *d_o = nullptr;
+    size_t cnt = (size_t)n * batch;
+    CK(cudaMalloc(&d_l, cnt * sizeof(double)));
+    CK(cudaMalloc(&d_o, cnt * sizeof(double)));
+    CK(cudaMalloc(&d_k, P * sizeof(double)));
+    cudaMemcpyAsync(d_l, lines, cnt * sizeof(double), cudaMemcpyDefault, c->stream);
+    cudaMemcpyAsync(d_k, hk.data(), P * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    size_t smem = ((size_t)P + n) * sizeof(double);
+    int rc = 0;
+    if (smem > 200 * 1024) rc = fail(D3D_EINVAL, "d3d_conv1d: line too long (%d)", n);
+    if (!rc) {
+        cudaFuncSetAttribute(conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv1d_kernel<<<(unsigned)std::min(batch, 148 * 8), 128, smem, c->stream>>>(d_l, d_k, d_o, n, P, batch);
+        c->launches++;
+        cudaMemcpyAsync(out, d_o, cnt * sizeof(double), cudaMemcpyDefault, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(D3D_ECUDA, "d3d_conv1d failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_l); cudaFree(d_o); cudaFree(d_k);
+    return rc;
+}
+
+extern "C" int d3d_rtnorm(d3d_ctx* c, int n, const double* a, const double* b, const double* mu,
+                          const double* sigma, uint64_t seed, uint32_t chain, uint32_t sweep,
+                          double* out, int32_t* used_out) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    if (!c->have_tables) return fail(D3D_ESTATE, "d3d_rtnorm needs d3d_set_rtnorm_tables");
+    if (n < 1 || !a || !b || !mu || !sigma || !out) return fail(D3D_EINVAL, "d3d_rtnorm: bad argument");
+    CK(cudaSetDevice(c->device));
+    double* d = nullptr; int* d_used = nullptr; int* d_status = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * 5 * sizeof(double)));
+    CK(cudaMalloc(&d_used, (size_t)(n + 1) * sizeof(int)));
+    d_status = d_used + n;
+    cudaMemsetAsync(d_status, 0, sizeof(int), c->stream);
+    const double* src[4] = {a, b, mu, sigma};
+    for (int j = 0; j < 4; ++j)
+        cudaMemcpyAsync(d + (size_t)j * n, src[j], (size_t)n * sizeof(double), cudaMemcpyDefault, c->stream);
+    rtnorm_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->pb.rt, n, d, d + n, d + 2 * (size_t)n,
+                                                          d + 3 * (size_t)n, seed, chain, sweep,
+                                                          d + 4 * (size_t)n, d_used, d_status);
+    c->launches++;
+    int h_status = 0;
+    cudaMemcpyAsync(out, d + 4 * (size_t)n, (size_t)n * sizeof(double), cudaMemcpyDefault, c->stream);
+    if (used_out) cudaMemcpyAsync(used_out, d_used, (size_t)n * sizeof(int), cudaMemcpyDefault, c->stream);
+    cudaMemcpyAsync(&h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d); cudaFree(d_used);
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_rtnorm failed: %s", cudaGetErrorString(e));
+    if (h_status) return fail(D3D_ENUMERIC, "Truncated ndst in [a,b]: b MUST be greater than a (or NaN bounds)");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+extern "C" int d3d_delta_logl(d3d_ctx* c, int chain, int y, int x, const double p_new[3],
+                              double out[3]) {
+    if (!c || !c->have_problem || !c->have_params)
+        return fail(D3D_ESTATE, "d3d_delta_logl needs a problem and parameters");
+    const Problem& pb = c->pb;
+    if (chain < 0 || chain >= pb.n_chains || y < 0 || y >= pb.H || x < 0 || x >= pb.W || !p_new || !out)
+        return fail(D3D_EINVAL, "d3d_delta_logl: bad argument");
+    CK(cudaSetDevice(c->device));
+    double* d_out = nullptr;
+    CK(cudaMalloc(&d_out, 3 * sizeof(double)));
+    EvalReq ev;
+    ev.enabled = 1; ev.p_new[0] = p_new[0]; ev.p_new[1] = p_new[1]; ev.p_new[2] = p_new[2];
+    ev.out = d_out;
+    const int site = y * pb.W + x;
+    size_t smem = c->sweep_smem;
+#define LAUNCH_EVAL(T, IV)                                                                        \
+    do {                                                                                          \
+        cudaFuncSetAttribute(eval_kernel<T, IV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        eval_kernel<T, IV><<<1, c->threads, smem, c->stream>>>(pb, chain, site, ev);              \
+    } while (0)
+    if (c->dtype == D3D_F64) { if (pb.var_is_cube) LAUNCH_EVAL(double, true); else LAUNCH_EVAL(double, false); }
+    else { if (pb.var_is_cube) LAUNCH_EVAL(float, true); else LAUNCH_EVAL(float, false); }
+#undef LAUNCH_EVAL
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 3 * sizeof(double), cudaMemcpyDefault, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_delta_logl failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------
+template <typename T, bool IV, int NE>
+static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep, double min_rate,
+                              double* chain_dev, double* lik_dev, long long row_first,
+                              long long rows_local) {
+    cudaFuncSetAttribute(sweep_seq_kernel<T, IV, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)c->sweep_smem);
+    sweep_seq_kernel<T, IV, NE><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
+        c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+template <typename T, bool IV, int NE>
+static cudaError_t launch_colour(d3d_ctx* c, long long it, double* chain_dev, double* lik_dev,
+                                 long long rows_local, long long row_local) {
+    const Problem& pb = c->pb;
+    cudaFuncSetAttribute(sweep_colour_kernel<T, IV, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)c->sweep_smem);
+    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
+    dim3 grid(nly * nlx, pb.n_chains);
+    for (int cy = 0; cy < pb.fh; ++cy)
+        for (int cx = 0; cx < pb.fw; ++cx) {
+            if (cy >= pb.H || cx >= pb.W) continue;
+            sweep_colour_kernel<T, IV, NE><<<grid, c->threads, c->sweep_smem, c->stream>>>(
+                pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
+            c->launches++;
+        }
+    return cudaGetLastError();
+}
+
+#define DISPATCH_NE(FN, T, IV, ...)                                         \
+    (c->ne == 4    ? FN<T, IV, 4>(__VA_ARGS__)                              \
+     : c->ne == 8  ? FN<T, IV, 8>(__VA_ARGS__)                              \
+     : c->ne == 16 ? FN<T, IV, 16>(__VA_ARGS__)                             \
+                   : FN<T, IV, 0>(__VA_ARGS__))
+#define DISPATCH(FN, ...)                                                                   \
+    (c->dtype == D3D_F64                                                                    \
+         ? (c->pb.var_is_cube ? DISPATCH_NE(FN, double, true, __VA_ARGS__)                  \
+                              : DISPATCH_NE(FN, double, false, __VA_ARGS__))                \
+         : (c->pb.var_is_cube ? DISPATCH_NE(FN, float, true, __VA_ARGS__)                   \
+                              : DISPATCH_NE(FN, float, false, __VA_ARGS__)))
+
+extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iterations, int mode,
+                         int keep_one_in, int refresh_every, double min_acceptance_rate,
+                         double* chain_out, double* lik_out, int64_t n_rows,
+                         int64_t* accepted_out, int64_t* iterations_out, float* elapsed_ms) {
+    if (!c || !c->have_problem || !c->have_params)
+        return fail(D3D_ESTATE, "d3d_sweep needs d3d_set_problem and parameters (+ d3d_forward)");
+    if (!c->have_tables) return fail(D3D_ESTATE, "d3d_sweep needs d3d_set_rtnorm_tables");
+    if (keep_one_in < 1) return fail(D3D_EINVAL, "keep_one_in= MUST be a positive integer");   // :112
+    if (first_iteration < 1 || n_iterations < 0) return fail(D3D_EINVAL, "bad iteration range");
+    if (mode != D3D_SEQ_EXACT && mode != D3D_COLOURED) return fail(D3D_EINVAL, "bad mode");
+    if (first_iteration + n_iterations > 0xffffffffLL) return fail(D3D_EINVAL, "iteration counter exceeds 32 bits");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    const size_t HW = (size_t)pb.H * pb.W;
+    const long long it_begin = first_iteration, it_end = first_iteration + n_iterations;
+
+    // rows written by this call: it / keep for it in [it_begin, it_end) with it % keep == 0
+    long long row_first = (it_begin + keep_one_in - 1) / keep_one_in;
+    long long row_last = (it_end - 1) / keep_one_in;            // inclusive
+    long long rows_local = n_iterations > 0 && row_last >= row_first ? row_last - row_first + 1 : 0;
+    if ((chain_out || lik_out) && rows_local > 0 && row_last >= n_rows)
+        return fail(D3D_EINVAL, "chain_out/lik_out have %lld rows, iteration %lld needs row %lld",
+                    (long long)n_rows, (long long)(row_last * keep_one_in), row_last);
+    double* chain_dev = nullptr; double* lik_dev = nullptr;
+    int rc = 0;
+    if (chain_out && rows_local > 0) {
+        if (cudaMalloc(&chain_dev, (size_t)pb.n_chains * rows_local * HW * 3 * sizeof(double)) != cudaSuccess)
+            return fail(D3D_ENOMEM, "Not enough device memory for that many iterations. Use a higher value in the keep_one_in= parameter.");
+        cudaMemsetAsync(chain_dev, 0, (size_t)pb.n_chains * rows_local * HW * 3 * sizeof(double), c->stream);
+    }
+    if (lik_out && rows_local > 0) {
+        if (cudaMalloc(&lik_dev, (size_t)pb.n_chains * rows_local * HW * sizeof(double)) != cudaSuccess) {
+            if (chain_dev) cudaFree(chain_dev);
+            return fail(D3D_ENOMEM, "Not enough device memory for the likelihood chain.");
+        }
+        cudaMemsetAsync(lik_dev, 0, (size_t)pb.n_chains * rows_local * HW * sizeof(double), c->stream);
+    }
+
+    cudaEventRecord(c->ev0, c->stream);
+    cudaError_t e = cudaSuccess;
+    long long it = it_begin;
+    while (it < it_end && e == cudaSuccess && !rc) {
+        // segment ends right after an iteration with it % refresh_every == 0 (lib/run.py:525)
+        long long seg_end = it_end;
+        if (refresh_every > 0) {
+            long long next_refresh = ((it + refresh_every - 1) / refresh_every) * refresh_every;
+            seg_end = std::min(it_end, next_refresh + 1);
+        }
+        if (mode == D3D_SEQ_EXACT) {
+            e = DISPATCH(launch_seq, c, it, seg_end, keep_one_in, min_acceptance_rate, chain_dev,
+                         lik_dev, row_first, rows_local);
+        } else {
+            for (long long k = it; k < seg_end && e == cudaSuccess; ++k) {
+                sweep_begin_kernel<<<(pb.n_chains + 127) / 128, 128, 0, c->stream>>>(pb, k, min_acceptance_rate);
+                c->launches++;
+                const bool save = (k % keep_one_in) == 0;
+                e = DISPATCH(launch_colour, c, k, save ? chain_dev : nullptr, save ? lik_dev : nullptr,
+                             rows_local, save ? k / keep_one_in - row_first : 0);
+            }
+        }
+        if (e == cudaSuccess && refresh_every > 0 && (seg_end - 1) % refresh_every == 0)
+            rc = run_forward(c, pb.params, 1, nullptr, 1, nullptr);
+        it = seg_end;
+    }
+    cudaEventRecord(c->ev1, c->stream);
+    if (e != cudaSuccess && !rc) rc = fail(D3D_ECUDA, "sweep launch failed: %s", cudaGetErrorString(e));
+
+    // copy the recorded rows to the caller's [n_chains][n_rows] arrays
+    if (!rc && rows_local > 0) {
+        for (int k = 0; k < pb.n_chains && !rc; ++k) {
+            if (chain_dev) {
+                e = cudaMemcpyAsync(chain_out + ((size_t)k * n_rows + row_first) * HW * 3,
+                                    chain_dev + (size_t)k * rows_local * HW * 3,
+                                    (size_t)rows_local * HW * 3 * sizeof(double), cudaMemcpyDefault, c->stream);
+                if (e != cudaSuccess) rc = fail(D3D_ECUDA, "chain copy failed: %s", cudaGetErrorString(e));
+            }
+            if (lik_dev && !rc) {
+                e = cudaMemcpyAsync(lik_out + ((size_t)k * n_rows + row_first) * HW,
+                                    lik_dev + (size_t)k * rows_local * HW,
+                                    (size_t)rows_local * HW * sizeof(double), cudaMemcpyDefault, c->stream);
+                if (e != cudaSuccess) rc = fail(D3D_ECUDA, "likelihood copy failed: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    std::vector<long long> h_acc(pb.n_chains), h_it(pb.n_chains);
+    int h_status = 0;
+    if (!rc) {
+        cudaMemcpyAsync(h_acc.data(), pb.accepted, pb.n_chains * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(h_it.data(), pb.iters, pb.n_chains * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(&h_status, pb.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    }
+    e = cudaStreamSynchronize(c->stream);
+    if (chain_dev) cudaFree(chain_dev);
+    if (lik_dev) cudaFree(lik_dev);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
+    if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, c->ev0, c->ev1);
+    long long updates = 0;
+    for (int k = 0; k < pb.n_chains; ++k) {
+        if (accepted_out) accepted_out[k] = h_acc[k];
+        if (iterations_out) iterations_out[k] = h_it[k];
+        updates += (h_it[k] - it_begin) * (long long)c->h_nsites[k / pb.chains_per_cube];
+    }
+    c->last_updates = updates;
+    c->last_bytes = (int64_t)((pb.var_is_cube ? 3 : 2) * (double)c->elem() *
+                              (double)c->window_voxels_per_sweep * (double)n_iterations);
+    if (h_status)
+        return fail(D3D_ENUMERIC, "cannot convert float NaN to integer: a NaN reached the truncated-normal sampler "
+                                  "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");
+    return 0;
+}
+
+extern "C" int d3d_get_counters(d3d_ctx* c, int64_t* kernel_launches, int64_t* last_sweep_bytes,
+                                int64_t* last_sweep_site_updates) {
+    if (!c) return fail(D3D_EINVAL, "ctx is NULL");
+    if (kernel_launches) *kernel_launches = c->launches;
+    if (last_sweep_bytes) *last_sweep_bytes = c->last_bytes;
+    if (last_sweep_site_updates) *last_sweep_site_updates = c->last_updates;
+    return 0;
+}

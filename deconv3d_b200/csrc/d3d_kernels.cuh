@@ -1,0 +1,775 @@
+// d3d_kernels.cuh -- sm_100a kernels of the deconv3d likelihood hot path.
+//
+// Device data layout (DESIGN.md "Data layout in HBM"): every cube is stored
+// z-fastest, [y][x][Dp] with Dp = D rounded up to the 16-byte vector width of
+// the storage type T (double2 / float4), so that the FSF window of a proposal
+// is wh runs of ww*Dp contiguous elements and a spaxel spectrum is one vector
+// run.  Padded channels hold zeros everywhere (data, 1/variance, residual).
+//
+// Maths of one site update (identical to lib/run.py:367-519, without the
+// full-cube temporaries):
+//   F = FSF window, Lu(c,w) = lsf (*) exp(-(z-c)^2/(2w^2))   (unit amplitude)
+//   h[z]  = sum_s F[s] iv[z,s] e[z,s]       G[z] = sum_s F[s]^2 iv[z,s]
+//   dLu   = Lu_old - Lu_new
+//   delta = ar_old - ar_new = -( a*sum_z dLu h  +  a^2/2 * sum_z dLu^2 G )
+//   Gibbs (L_end = accepted ? Lu_new : Lu_old):
+//     S2 = sum_z L_end^2 G ,  S1 = sum_z L_end (h + a Lu_old G)
+//     ro = ra/(1+ra S2), mu = ro S1, r ~ TN(mu, sqrt(ro); [a_min, a_max])
+//   e <- e + F (a Lu_old - r L_end)
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "d3d_rng.cuh"
+
+namespace d3d {
+
+template <typename T> struct Vec;
+template <> struct Vec<double> { typedef double2 V; static const int N = 2; };
+template <> struct Vec<float>  { typedef float4  V; static const int N = 4; };
+
+__device__ __forceinline__ void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ void unpack(const float4& v, double* o) {
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void pack(double2& v, const double* o) { v.x = o[0]; v.y = o[1]; }
+__device__ __forceinline__ void pack(float4& v, const double* o) {
+    v.x = (float)o[0]; v.y = (float)o[1]; v.z = (float)o[2]; v.w = (float)o[3];
+}
+
+struct Problem {
+    int D, Dp, H, W, fh, fw, fhh, fhw, P;
+    int n_cubes, chains_per_cube, n_chains;
+    int var_is_cube, has_lsf, max_sites;
+    const void* data;          // [cube][H][W][Dp] T
+    const void* iv;            // [cube][H][W][Dp] T   (var_is_cube)
+    const double* iv_scalar;   // [cube]               (!var_is_cube)
+    void* err;                 // [chain][H][W][Dp] T
+    double* params;            // [chain][H][W][3]
+    const uint8_t* mask;       // [cube][H][W]
+    const int* sites;          // [cube][max_sites]  linear y*W+x, row-major (lib/run.py:553-566)
+    const int* n_sites;        // [cube]
+    const double* fsf;         // [fh*fw]
+    const double* kcirc;       // [P] circular LSF kernel (lib/convolution.py:89-160 in direct form)
+    const double* pmin;        // [cube][3]
+    const double* pmax;        // [cube][3]
+    const double* prior_var;   // [cube]
+    double jump[3];
+    RtTables rt;
+    unsigned long long seed;
+    unsigned int first_chain;
+    long long* accepted;       // [chain]  accepted_count           (lib/run.py:341,440)
+    long long* iters;          // [chain]  cur_iteration reached
+    double* rate;              // [chain]  cur_acceptance_rate      (lib/run.py:356-359)
+    int* active;               // [chain]
+    int* status;               // [1] sticky numeric-failure flag
+};
+
+// One proposal evaluated without touching any state (d3d_delta_logl).
+struct EvalReq {
+    int enabled;
+    double p_new[3];
+    double* out;               // [3] delta, ar_old, ar_new
+};
+
+// Shared-memory carve-up, all doubles.
+struct Smem {
+    double* F;      // [fh*fw]
+    double* K;      // [P]
+    double* g_o;    // [Dp]
+    double* g_n;    // [Dp]
+    double* Lu_o;   // [Dp]
+    double* Lu_n;   // [Dp]
+    double* red;    // [32][8]
+    double* bc;     // [8]
+};
+
+__host__ __device__ inline size_t smem_doubles(int fh, int fw, int P, int Dp) {
+    return (size_t)fh * fw + P + 4 * (size_t)Dp + 32 * 8 + 8;
+}
+
+__device__ __forceinline__ void carve(Smem& s, double* base, const Problem& pb) {
+    s.F = base;
+    s.K = s.F + pb.fh * pb.fw;
+    s.g_o = s.K + pb.P;
+    s.g_n = s.g_o + pb.Dp;
+    s.Lu_o = s.g_n + pb.Dp;
+    s.Lu_n = s.Lu_o + pb.Dp;
+    s.red = s.Lu_n + pb.Dp;
+    s.bc = s.red + 32 * 8;
+}
+
+__device__ __forceinline__ void load_constants(Smem& s, const Problem& pb) {
+    for (int i = threadIdx.x; i < pb.fh * pb.fw; i += blockDim.x) s.F[i] = pb.fsf[i];
+    for (int i = threadIdx.x; i < pb.P; i += blockDim.x) s.K[i] = pb.kcirc[i];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// lib/line_models.py:98-109 with a = 1
+__device__ __forceinline__ double unit_gaussian(int z, double c, double w) {
+    double d = (double)z - c;
+    return exp(-1.0 * (d * d) / (2.0 * (w * w)));
+}
+
+// lib/convolution.py:89-120 in direct form: out[j] = sum_i g[i] K[(j-i) mod P]
+__device__ __forceinline__ double conv_at(const double* g, const double* K, int j, int D, int P) {
+    double acc = 0.0;
+    for (int i = 0; i < D; ++i) acc = fma(g[i], K[(j - i) & (P - 1)], acc);
+    return acc;
+}
+
+enum { R_B = 0, R_C, R_PO, R_QOO, R_QON, R_QNN, R_A, R_N };
+
+// ---------------------------------------------------------------------------
+// One MH-within-Gibbs site update by one CTA.  NE > 0: the residual window is
+// kept in registers between the reduction and the update (NE vectors/thread);
+// NE == 0: it is re-read (L1/L2) for the update.
+// Returns (to all threads) whether the proposal was accepted.
+// ---------------------------------------------------------------------------
+template <typename T, bool IVCUBE, int NE, bool WANT_AR>
+__device__ __forceinline__ int site_update(const Problem& pb, const Smem& sm, int chain, int cube,
+                                           int site, unsigned int sweep, double* chain_row,
+                                           double* lik_row, const EvalReq& ev) {
+    typedef typename Vec<T>::V V;
+    const int VEC = Vec<T>::N;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
+    const int D = pb.D, Dp = pb.Dp, W = pb.W, H = pb.H;
+    const int y = site / W, x = site - y * W;
+
+    // ---- proposal (lib/run.py:370-388, 570-579) and line profiles ------------
+    double* prm = pb.params + ((size_t)chain * H * W + site) * 3;
+    const double a = prm[0], c_old = prm[1], w_old = prm[2];
+    double c_new = c_old, w_new = w_old, a_new = a, log_u = 0.0;
+    int oob = 0;
+    Philox rng;
+    const int nprep = Dp > 32 ? Dp : 32;
+    if (tid < nprep) {
+        if (ev.enabled) {
+            a_new = ev.p_new[0]; c_new = ev.p_new[1]; w_new = ev.p_new[2];
+        } else {
+            rng.init(pb.seed, pb.first_chain + (unsigned)chain, sweep, (unsigned)site);
+            const double q4 = 1.5707963267948966;                   // CIRCLE_4TH, lib/run.py:35
+            double u0 = rng.next(), u1 = rng.next(), u2 = rng.next();
+            (void)u0;                                               // amplitude jump is 0 (:262)
+            if (pb.jump[0] != 0.0) a_new = a + pb.jump[0] * tan(-q4 + (q4 - (-q4)) * u0);
+            c_new = c_old + pb.jump[1] * tan(-q4 + (q4 - (-q4)) * u1);
+            w_new = w_old + pb.jump[2] * tan(-q4 + (q4 - (-q4)) * u2);
+            log_u = log(rng.next());                                // :435
+        }
+        const double* lo = pb.pmin + cube * 3;
+        const double* hi = pb.pmax + cube * 3;
+        oob = (a_new < lo[0]) | (c_new < lo[1]) | (w_new < lo[2]) |
+              (a_new > hi[0]) | (c_new > hi[1]) | (w_new > hi[2]);  // :379-384
+        if (tid < Dp) {
+            sm.g_o[tid] = tid < D ? unit_gaussian(tid, c_old, w_old) : 0.0;
+            sm.g_n[tid] = tid < D ? unit_gaussian(tid, c_new, w_new) : 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid < Dp) {
+        double lo_ = 0.0, ln_ = 0.0;
+        if (tid < D) {
+            if (pb.has_lsf) {
+                lo_ = conv_at(sm.g_o, sm.K, tid, D, pb.P);
+                ln_ = conv_at(sm.g_n, sm.K, tid, D, pb.P);
+            } else {                                                // lib/run.py:675-676
+                lo_ = sm.g_o[tid]; ln_ = sm.g_n[tid];
+            }
+        }
+        sm.Lu_o[tid] = lo_;
+        sm.Lu_n[tid] = ln_;
+    }
+    __syncthreads();
+
+    // ---- window geometry (lib/run.py:407-410) --------------------------------
+    const int y0 = max(y - pb.fhh, 0), y1 = min(y + pb.fhh + 1, H);
+    const int x0 = max(x - pb.fhw, 0), x1 = min(x + pb.fhw + 1, W);
+    const int ww = x1 - x0, npos = (y1 - y0) * ww;
+    const int oy = y0 - (y - pb.fhh), ox = x0 - (x - pb.fhw);
+    const int ZL = Dp / VEC;
+    const int NC = blockDim.x / ZL;
+    const int col = tid / ZL, zp = tid - col * ZL;
+    const bool worker = col < NC;
+    const int stepy = NC / ww, stepx = NC - stepy * ww;
+
+    T* err = (T*)pb.err + (size_t)chain * H * W * Dp;
+    const T* ivc = IVCUBE ? (const T*)pb.iv + (size_t)cube * H * W * Dp : nullptr;
+    const double ivs = IVCUBE ? 0.0 : pb.iv_scalar[cube];
+
+    double h[VEC], g[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
+    double f2 = 0.0, A = 0.0;
+    V ecache[NE > 0 ? NE : 1];
+
+    if (worker) {
+        int dy = col / ww, dx = col - dy * ww;
+        if (NE > 0) {
+            // chunks of CH window vectors: all loads of a chunk are issued before its
+            // arithmetic (memory-level parallelism), the residual stays in registers
+            const int CH = 4;
+#pragma unroll
+            for (int i0 = 0; i0 < NE; i0 += CH) {
+                V ivch[IVCUBE ? CH : 1];
+                double fch[CH];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int i = i0 + j;
+                    if (i < NE) {
+                        const int q = col + i * NC;
+                        if (q < npos) {
+                            size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                            ecache[i] = *(const V*)(err + off);
+                            if (IVCUBE) ivch[j] = *(const V*)(ivc + off);
+                            fch[j] = sm.F[(oy + dy) * pb.fw + ox + dx];
+                        } else {          // outside the clipped window: contributes nothing
+                            fch[j] = 0.0;
+                            ecache[i] = V();
+                            if (IVCUBE) ivch[j] = V();
+                        }
+                        dx += stepx; dy += stepy;
+                        if (dx >= ww) { dx -= ww; ++dy; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CH; ++j) {
+                    const int i = i0 + j;
+                    if (i < NE) {
+                        const double f = fch[j];
+                        double e[VEC];
+                        unpack(ecache[i], e);
+                        if (IVCUBE) {
+                            double w_[VEC];
+                            unpack(ivch[j], w_);
+                            const double ff = f * f;
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                double t = w_[v] * e[v];
+                                h[v] = fma(f, t, h[v]);
+                                g[v] = fma(ff, w_[v], g[v]);
+                                if (WANT_AR) A = fma(t, e[v], A);
+                            }
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                h[v] = fma(f, e[v], h[v]);
+                                if (WANT_AR) A = fma(e[v], e[v], A);
+                            }
+                            f2 = fma(f, f, f2);
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int q = col; q < npos; q += NC) {
+                size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+                double e[VEC];
+                unpack(*(const V*)(err + off), e);
+                if (IVCUBE) {
+                    double w_[VEC];
+                    unpack(*(const V*)(ivc + off), w_);
+                    const double ff = f * f;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        double t = w_[v] * e[v];
+                        h[v] = fma(f, t, h[v]);
+                        g[v] = fma(ff, w_[v], g[v]);
+                        if (WANT_AR) A = fma(t, e[v], A);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        h[v] = fma(f, e[v], h[v]);
+                        if (WANT_AR) A = fma(e[v], e[v], A);
+                    }
+                    f2 = fma(f, f, f2);
+                }
+                dx += stepx; dy += stepy;
+                if (dx >= ww) { dx -= ww; ++dy; }
+            }
+        }
+    }
+
+    // ---- per-thread partials of the six (seven) sums --------------------------
+    double part[R_N];
+#pragma unroll
+    for (int j = 0; j < R_N; ++j) part[j] = 0.0;
+    double lo_v[VEC], ln_v[VEC];
+    if (worker) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            lo_v[v] = sm.Lu_o[zp * VEC + v];
+            ln_v[v] = sm.Lu_n[zp * VEC + v];
+            const double dl = lo_v[v] - ln_v[v];
+            const double hv = IVCUBE ? h[v] : ivs * h[v];
+            const double gv = IVCUBE ? g[v] : ivs * f2;
+            part[R_B] = fma(dl, hv, part[R_B]);
+            part[R_PO] = fma(lo_v[v], hv, part[R_PO]);
+            part[R_C] = fma(dl * dl, gv, part[R_C]);
+            part[R_QOO] = fma(lo_v[v] * lo_v[v], gv, part[R_QOO]);
+            part[R_QON] = fma(lo_v[v] * ln_v[v], gv, part[R_QON]);
+            part[R_QNN] = fma(ln_v[v] * ln_v[v], gv, part[R_QNN]);
+        }
+        if (WANT_AR) part[R_A] = IVCUBE ? A : ivs * A;
+    } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { lo_v[v] = 0.0; ln_v[v] = 0.0; }
+    }
+#pragma unroll
+    for (int j = 0; j < R_N; ++j) {
+        if (j == R_A && !WANT_AR) continue;
+        double s = warp_sum(part[j]);
+        if (lane == 0) sm.red[warp * 8 + j] = s;
+    }
+    __syncthreads();
+
+    // ---- decision by warp 0 (lib/run.py:426-451, 456-499) ---------------------
+    if (warp == 0) {
+        double tot[R_N];
+#pragma unroll
+        for (int j = 0; j < R_N; ++j) {
+            if (j == R_A && !WANT_AR) { tot[j] = 0.0; continue; }
+            tot[j] = warp_sum(lane < nwarps ? sm.red[lane * 8 + j] : 0.0);
+        }
+        const double da = ev.enabled ? a_new : a;    // evaluation may also move the amplitude
+        double delta;
+        if (a_new != a) {
+            // general amplitude change: delta L = a Lu_o - a_new Lu_n
+            // sum dL h = a Po - a_new Pn ; sum dL^2 G = a^2 Qoo - 2 a a_new Qon + a_new^2 Qnn
+            const double Pn = tot[R_PO] - tot[R_B];
+            const double Bq = a * tot[R_PO] - da * Pn;
+            const double Cq = a * a * tot[R_QOO] - 2.0 * a * da * tot[R_QON] + da * da * tot[R_QNN];
+            delta = -Bq - 0.5 * Cq;
+        } else {
+            delta = -(a * tot[R_B]) - 0.5 * (a * a) * tot[R_C];
+        }
+        if (ev.enabled) {
+            if (lane == 0) {
+                const double ar_old = 0.5 * tot[R_A];
+                ev.out[0] = delta; ev.out[1] = ar_old; ev.out[2] = ar_old - delta;
+            }
+            sm.bc[0] = 0.0;
+        } else {
+            const int accepted = (log_u < delta) && !oob;           // :438
+            const double c_end = accepted ? c_new : c_old;
+            const double w_end = accepted ? w_new : w_old;
+            const double S2 = accepted ? tot[R_QNN] : tot[R_QOO];
+            const double S1 = accepted ? (tot[R_PO] - tot[R_B]) + a * tot[R_QON]
+                                       : tot[R_PO] + a * tot[R_QOO];
+            const double ra = pb.prior_var[cube];                   // :491
+            const double ro = ra / (1.0 + ra * S2);                 // :492
+            const double mu = ro * S1;                              // :493
+            int fail = 0;
+            const double r = rtnorm(pb.pmin[cube * 3], pb.pmax[cube * 3], mu, sqrt(ro), rng,
+                                    pb.rt, &fail);                  // :495-496
+            if (lane == 0) {
+                if (fail) atomicExch(pb.status, 1);
+                prm[0] = r; prm[1] = c_end; prm[2] = w_end;         // :448, :499, :516
+                if (chain_row) { chain_row[0] = r; chain_row[1] = c_end; chain_row[2] = w_end; }
+                if (lik_row) *lik_row = delta;                      // :430-432
+                sm.bc[0] = accepted ? 1.0 : 0.0;
+                sm.bc[1] = r;
+            }
+        }
+    }
+    __syncthreads();
+    if (ev.enabled) return 0;
+    const int accepted = sm.bc[0] != 0.0;
+    const double r = sm.bc[1];
+
+    // ---- residual update: e <- e + F (a Lu_old - r L_end)  (:402,:441,:508-515) -
+    if (worker) {
+        double coef[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) coef[v] = a * lo_v[v] - r * (accepted ? ln_v[v] : lo_v[v]);
+        int dy = col / ww, dx = col - dy * ww;
+        if (NE > 0) {
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                int q = col + i * NC;
+                if (q < npos) {
+                    size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                    const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+                    double e[VEC];
+                    unpack(ecache[i], e);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                    V o;
+                    pack(o, e);
+                    *(V*)(err + off) = o;
+                }
+                dx += stepx; dy += stepy;
+                if (dx >= ww) { dx -= ww; ++dy; }
+            }
+        } else {
+            for (int q = col; q < npos; q += NC) {
+                size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+                double e[VEC];
+                unpack(*(const V*)(err + off), e);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                V o;
+                pack(o, e);
+                *(V*)(err + off) = o;
+                dx += stepx; dy += stepy;
+                if (dx >= ww) { dx -= ww; ++dy; }
+            }
+        }
+    }
+    return accepted;
+}
+
+// ---------------------------------------------------------------------------
+// SEQ_EXACT: one CTA per chain walks the masked spaxels in the reference's
+// row-major order for iterations [it0, it1) (lib/run.py:344-537).
+// ---------------------------------------------------------------------------
+template <typename T, bool IVCUBE, int NE>
+__global__ void sweep_seq_kernel(Problem pb, long long it0, long long it1, int keep,
+                                 double min_rate, double* chain_out, double* lik_out,
+                                 long long row_first, long long rows_local) {
+    extern __shared__ double smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    const int chain = blockIdx.x;
+    if (chain >= pb.n_chains) return;
+    const int cube = chain / pb.chains_per_cube;
+    if (!pb.active[chain]) return;
+    load_constants(sm, pb);
+    __syncthreads();
+
+    const int ns = pb.n_sites[cube];
+    const int* sites = pb.sites + (size_t)cube * pb.max_sites;
+    long long accepted = pb.accepted[chain];
+    double rate = pb.rate[chain];
+    const size_t HW = (size_t)pb.H * pb.W;
+    EvalReq ev; ev.enabled = 0; ev.out = nullptr;
+    long long it = it0;
+    int alive = 1;
+    for (; it < it1; ++it) {
+        if (!(rate > min_rate || rate == 0.0)) { alive = 0; break; }   // :344-350
+        const double max_acc = (double)ns * (double)it;                // :356-359
+        if (max_acc > 0.0) rate = (double)accepted / max_acc;
+        const bool save = (it % keep) == 0;                            // :353
+        double* crow = nullptr; double* lrow = nullptr;
+        if (save) {
+            long long r = it / keep - row_first;
+            if (chain_out) crow = chain_out + ((size_t)chain * rows_local + r) * HW * 3;
+            if (lik_out) lrow = lik_out + ((size_t)chain * rows_local + r) * HW;
+        }
+        for (int s = 0; s < ns; ++s) {
+            const int site = sites[s];
+            accepted += site_update<T, IVCUBE, NE, false>(
+                pb, sm, chain, cube, site, (unsigned)it, crow ? crow + (size_t)site * 3 : nullptr,
+                lrow ? lrow + site : nullptr, ev);
+        }
+    }
+    if (threadIdx.x == 0) {
+        pb.accepted[chain] = accepted;
+        pb.rate[chain] = rate;
+        pb.iters[chain] = it;
+        if (!alive) pb.active[chain] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// COLOURED: one launch per colour class (cy, cx) = (y mod fh, x mod fw); the
+// windows of the sites of one class are pairwise disjoint, so one CTA per
+// (site, chain) updates them concurrently.  sweep_begin_kernel evaluates the
+// loop condition of lib/run.py:344-359 once per iteration.
+// ---------------------------------------------------------------------------
+__global__ void sweep_begin_kernel(Problem pb, long long it, double min_rate) {
+    int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= pb.n_chains || !pb.active[chain]) return;
+    double rate = pb.rate[chain];
+    if (!(rate > min_rate || rate == 0.0)) { pb.active[chain] = 0; pb.iters[chain] = it; return; }
+    double max_acc = (double)pb.n_sites[chain / pb.chains_per_cube] * (double)it;
+    if (max_acc > 0.0) pb.rate[chain] = (double)pb.accepted[chain] / max_acc;
+    pb.iters[chain] = it + 1;
+}
+
+template <typename T, bool IVCUBE, int NE>
+__global__ void sweep_colour_kernel(Problem pb, long long it, int cy, int cx, int nlx,
+                                    double* crow_base, double* lrow_base, long long rows_local,
+                                    long long row_local) {
+    extern __shared__ double smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    const int chain = blockIdx.y;
+    const int cube = chain / pb.chains_per_cube;
+    const int iy = blockIdx.x / nlx, ix = blockIdx.x - iy * nlx;
+    const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;
+    if (y >= pb.H || x >= pb.W) return;
+    if (!pb.active[chain]) return;
+    const int site = y * pb.W + x;
+    if (pb.mask[(size_t)cube * pb.H * pb.W + site] != 1) return;
+    load_constants(sm, pb);
+    __syncthreads();
+    const size_t HW = (size_t)pb.H * pb.W;
+    double* crow = crow_base ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3
+                             : nullptr;
+    double* lrow = lrow_base ? lrow_base + ((size_t)chain * rows_local + row_local) * HW + site
+                             : nullptr;
+    EvalReq ev; ev.enabled = 0; ev.out = nullptr;
+    int acc = site_update<T, IVCUBE, NE, false>(pb, sm, chain, cube, site, (unsigned)it, crow, lrow,
+                                                ev);
+    if (threadIdx.x == 0 && acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+}
+
+template <typename T, bool IVCUBE>
+__global__ void eval_kernel(Problem pb, int chain, int site, EvalReq ev) {
+    extern __shared__ double smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    load_constants(sm, pb);
+    __syncthreads();
+    site_update<T, IVCUBE, 0, true>(pb, sm, chain, chain / pb.chains_per_cube, site, 0u, nullptr,
+                                    nullptr, ev);
+}
+
+// ---------------------------------------------------------------------------
+// Forward model (lib/run.py:999-1031 / 623-652)
+// ---------------------------------------------------------------------------
+// Pass 1 (spectral): lines[chain][y][x][Dp] = mask * a * (lsf (*) gaussian(c,w)); one warp
+// per spaxel, the Gaussian is exchanged through shared memory.
+__global__ void lines_kernel(Problem pb, const double* params, double* lines, int convolve) {
+    extern __shared__ double smem_raw[];
+    double* K = smem_raw;                         // [P]
+    double* g = K + pb.P;                         // [warps][Dp]
+    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < pb.P; i += blockDim.x) K[i] = pb.kcirc[i];
+    __syncthreads();
+    const size_t HW = (size_t)pb.H * pb.W;
+    const size_t total = (size_t)pb.n_chains * HW;
+    double* gw = g + (size_t)warp * pb.Dp;
+    for (size_t sp = (size_t)blockIdx.x * wpb + warp; sp < total; sp += (size_t)gridDim.x * wpb) {
+        const int chain = (int)(sp / HW);
+        const size_t site = sp - (size_t)chain * HW;
+        const int cube = chain / pb.chains_per_cube;
+        const bool on = pb.mask[(size_t)cube * HW + site] == 1;
+        const double* p = params + sp * 3;
+        const double a = p[0], c = p[1], w = p[2];
+        double* out = lines + sp * pb.Dp;
+        if (!on) {
+            for (int z = lane; z < pb.Dp; z += 32) out[z] = 0.0;
+            continue;
+        }
+        for (int z = lane; z < pb.Dp; z += 32)
+            gw[z] = z < pb.D ? a * unit_gaussian(z, c, w) : 0.0;     // lib/line_models.py:109
+        __syncwarp();
+        for (int z = lane; z < pb.Dp; z += 32) {
+            double v = 0.0;
+            if (z < pb.D) v = (convolve && pb.has_lsf) ? conv_at(gw, K, z, pb.D, pb.P) : gw[z];
+            out[z] = v;
+        }
+        __syncwarp();
+    }
+}
+
+// Pass 2 (spatial): true 2-D convolution with the FSF, zero 'same' borders
+// (scipy.signal.convolve2d(..., 'same'), lib/run.py:1027-1029, equal to the paste
+// at lib/run.py:697-706).  CTA = TY x TX output spaxels x ZC channels; the
+// (TY+fh-1) x (TX+fw-1) halo tile of `lines` is staged in shared memory once and
+// every output accumulates fh*fw taps from it.  Fused epilogue: residual =
+// data - sim, optional sim output in the reference layout, optional chi^2.
+template <typename T>
+__global__ void stencil_zchunk_kernel(Problem pb, const double* lines, double* sim_out,
+                                      int write_err, double* chi2_out, int TY, int TX, int ZC) {
+    extern __shared__ double smem_raw[];
+    const int fh = pb.fh, fw = pb.fw, Dp = pb.Dp, D = pb.D, H = pb.H, W = pb.W;
+    double* F = smem_raw;                                  // [fh*fw]
+    double* tile = F + fh * fw;                            // [hy][hx][zc]
+    const int ty_n = (H + TY - 1) / TY, tx_n = (W + TX - 1) / TX;
+    const int chain = blockIdx.x / (ty_n * tx_n);
+    const int trem = blockIdx.x - chain * ty_n * tx_n;
+    const int ty0 = (trem / tx_n) * TY, tx0 = (trem % tx_n) * TX;
+    const int z0 = blockIdx.y * ZC;
+    const int zc = min(ZC, Dp - z0);
+    const int cube = chain / pb.chains_per_cube;
+    const int hy = TY + fh - 1, hx = TX + fw - 1;
+    for (int i = threadIdx.x; i < fh * fw; i += blockDim.x) F[i] = pb.fsf[i];
+    const double* lc = lines + (size_t)chain * H * W * Dp;
+    for (int i = threadIdx.x; i < hy * hx * zc; i += blockDim.x) {
+        int z = i % zc, s = i / zc;
+        int sy = s / hx, sx = s - sy * hx;
+        int gy = ty0 + sy - pb.fhh, gx = tx0 + sx - pb.fhw;
+        double v = 0.0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = lc[((size_t)gy * W + gx) * Dp + z0 + z];
+        tile[i] = v;
+    }
+    __syncthreads();
+    const T* data = (const T*)pb.data + (size_t)cube * H * W * Dp;
+    const T* ivc = pb.var_is_cube ? (const T*)pb.iv + (size_t)cube * H * W * Dp : nullptr;
+    const double ivs = pb.var_is_cube ? 0.0 : pb.iv_scalar[cube];
+    T* err = (T*)pb.err + (size_t)chain * H * W * Dp;
+    double chi = 0.0;
+    for (int i = threadIdx.x; i < TY * TX * zc; i += blockDim.x) {
+        int z = i % zc, s = i / zc;
+        int oy = s / TX, ox = s - oy * TX;
+        int gy = ty0 + oy, gx = tx0 + ox;
+        if (gy >= H || gx >= W) continue;
+        // sim[y',x'] = sum_{j,k} F[j][k] lines[y'+fhh-j][x'+fhw-k]   (lib/run.py:697-706)
+        double acc = 0.0;
+        for (int j = 0; j < fh; ++j) {
+            const double* trow = tile + ((size_t)(oy + fh - 1 - j) * hx + ox + fw - 1) * zc + z;
+            const double* frow = F + j * fw;
+            for (int k = 0; k < fw; ++k) acc = fma(frow[k], trow[-(ptrdiff_t)k * zc], acc);
+        }
+        const int zz = z0 + z;
+        size_t off = ((size_t)gy * W + gx) * Dp + zz;
+        if (sim_out && zz < D)
+            sim_out[(size_t)chain * D * H * W + ((size_t)zz * H + gy) * W + gx] = acc;
+        if (write_err || chi2_out) {
+            double e = (double)data[off] - acc;
+            if (zz >= D) e = 0.0;
+            if (write_err) err[off] = (T)e;
+            if (chi2_out) chi += e * e * (ivc ? (double)ivc[off] : ivs);
+        }
+    }
+    if (chi2_out) {
+        chi = warp_sum(chi);
+        if ((threadIdx.x & 31) == 0) atomicAdd(chi2_out + chain, 0.5 * chi);
+    }
+}
+
+// un-convolved lines in the reference layout (lib/run.py:597-621)
+__global__ void clean_kernel(Problem pb, const double* params, double* out) {
+    const size_t HW = (size_t)pb.H * pb.W;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)pb.n_chains * pb.D * HW;
+    if (i >= total) return;
+    size_t site = i % HW;
+    size_t r = i / HW;
+    int z = (int)(r % pb.D);
+    int chain = (int)(r / pb.D);
+    int cube = chain / pb.chains_per_cube;
+    double v = 0.0;
+    if (pb.mask[(size_t)cube * HW + site] == 1) {
+        const double* p = params + ((size_t)chain * HW + site) * 3;
+        v = p[0] * unit_gaussian(z, p[1], p[2]);
+    }
+    out[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// Layout conversion between the reference layout [n][D][H][W] float64 and the
+// device layout [n][H][W][Dp] T.
+//   mode 0: plain copy (data; NaN -> 0)          mode 1: reciprocal (variance -> 1/var;
+//   NaN/zero-weight voxels -> 0, and voxels whose data value is NaN -> 0)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void ingest_kernel(const double* src, const double* data_for_nan, T* dst, int n, int D,
+                              int Dp, int H, int W, int mode) {
+    // tile transpose through shared memory: read x-fastest, write z-fastest
+    __shared__ double tile[32][33];
+    const int nzt = (Dp + 31) / 32, nxt = (W + 31) / 32;
+    long long b = blockIdx.x;
+    const int xt = (int)(b % nxt); b /= nxt;
+    const int zt = (int)(b % nzt); b /= nzt;
+    const int y = (int)(b % H); b /= H;
+    const int cube = (int)b;
+    if (cube >= n) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        int z = zt * 32 + r, x = xt * 32 + tx;
+        double v = 0.0;
+        if (z < D && x < W) {
+            size_t si = (((size_t)cube * D + z) * H + y) * W + x;
+            v = src[si];
+            if (mode == 1) {
+                double dv = data_for_nan ? data_for_nan[si] : 0.0;
+                v = (v == v && dv == dv) ? 1.0 / v : 0.0;
+                if (!(v == v) || isinf(v)) v = 0.0;
+            } else if (!(v == v)) v = 0.0;
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int x = xt * 32 + r, z = zt * 32 + tx;
+        if (x < W && z < Dp)
+            dst[(((size_t)cube * H + y) * W + x) * Dp + z] = (T)tile[tx][r];
+    }
+}
+
+// device layout -> reference layout, float64 out
+template <typename T>
+__global__ void egest_kernel(const T* src, double* dst, int n, int D, int Dp, int H, int W) {
+    __shared__ double tile[32][33];
+    const int nzt = (Dp + 31) / 32, nxt = (W + 31) / 32;
+    long long b = blockIdx.x;
+    const int xt = (int)(b % nxt); b /= nxt;
+    const int zt = (int)(b % nzt); b /= nzt;
+    const int y = (int)(b % H); b /= H;
+    const int cube = (int)b;
+    if (cube >= n) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        int x = xt * 32 + r, z = zt * 32 + tx;
+        double v = 0.0;
+        if (x < W && z < Dp) v = (double)src[(((size_t)cube * H + y) * W + x) * Dp + z];
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int z = zt * 32 + r, x = xt * 32 + tx;
+        if (z < D && x < W) dst[(((size_t)cube * D + z) * H + y) * W + x] = tile[tx][r];
+    }
+}
+
+// Initial parameters uniform in the boundaries (lib/run.py:308-314), sweep 0.
+__global__ void init_params_kernel(Problem pb) {
+    const size_t HW = (size_t)pb.H * pb.W;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)pb.n_chains * HW) return;
+    const int chain = (int)(i / HW);
+    const int site = (int)(i - (size_t)chain * HW);
+    const int cube = chain / pb.chains_per_cube;
+    double* p = pb.params + i * 3;
+    if (pb.mask[(size_t)cube * HW + site] != 1) { p[0] = p[1] = p[2] = 0.0; return; }
+    Philox rng;
+    rng.init(pb.seed, pb.first_chain + (unsigned)chain, 0u, (unsigned)site);
+    for (int j = 0; j < 3; ++j) {
+        double lo = pb.pmin[cube * 3 + j], hi = pb.pmax[cube * 3 + j];
+        p[j] = lo + (hi - lo) * rng.next();
+    }
+}
+
+// Batched truncated normal (lib/rtnorm.py:21-92), one variate per thread.
+__global__ void rtnorm_kernel(RtTables rt, int n, const double* a, const double* b,
+                              const double* mu, const double* sigma, unsigned long long seed,
+                              unsigned int chain, unsigned int sweep, double* out, int* used,
+                              int* status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Philox rng;
+    rng.init(seed, chain, sweep, (unsigned)i);
+    int fail = 0;
+    out[i] = rtnorm(a[i], b[i], mu[i], sigma[i], rng, rt, &fail);
+    if (used) used[i] = (int)rng.k;
+    if (fail) atomicExch(status, 1);
+}
+
+// Batched spectral convolution (lib/convolution.py:89-120): out[b][j].
+__global__ void conv1d_kernel(const double* lines, const double* kcirc, double* out, int n, int P,
+                              int batch) {
+    extern __shared__ double smem_raw[];
+    double* K = smem_raw;
+    double* g = K + P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) K[i] = kcirc[i];
+    for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) g[i] = lines[(size_t)b * n + i];
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += blockDim.x)
+            out[(size_t)b * n + j] = conv_at(g, K, j, n, P);
+    }
+}
+
+}  // namespace d3d

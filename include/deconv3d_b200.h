@@ -1,0 +1,182 @@
+/*
+ * deconv3d_b200.h -- C ABI of libdeconv3d_b200.so
+ *
+ * B200 (sm_100a) implementation of the per-iteration likelihood hot path of
+ * irap-omp/deconv3d.  The reference is pure Python and has no FFI of its own
+ * (SURVEY.md section 8b): its boundary for this path is the Python object API
+ * of lib/run.py, lib/convolution.py, lib/line_models.py.  Each entry point
+ * below names the reference interface it replaces (paths relative to the
+ * reference tree); deconv3d_b200/_native.py is the ctypes binding and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative D3D_E* code; the
+ *     message is available from d3d_last_error() (thread-local).
+ *   - All array arguments are plain pointers owned by the caller and are only
+ *     borrowed for the duration of the call.  They may be host or device
+ *     pointers (the library copies with cudaMemcpyDefault).
+ *   - Host-visible arrays use the REFERENCE layouts and float64:
+ *       cubes        [n][D][H][W]      (z, y, x; x fastest)  lib/run.py:146-149
+ *       parameters   [n][H][W][3]      (a, c, w)             lib/run.py:270-272
+ *       chain rows   [n][rows][H][W][3], likelihood rows [n][rows][H][W]
+ *     Internally the residual lives z-fastest ([y][x][Dp]) in the storage
+ *     dtype chosen at d3d_ctx_create.
+ *   - A context is bound to one GPU and one stream; calls on one context must
+ *     be serialised by the caller.  No global state.
+ */
+#ifndef DECONV3D_B200_H
+#define DECONV3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3D_ABI_VERSION 1
+
+/* storage dtype of the residual / data / inverse-variance cubes */
+#define D3D_F32 0
+#define D3D_F64 1
+
+/* sweep modes */
+#define D3D_SEQ_EXACT 0   /* row-major masked order of lib/run.py:553-566, one CTA per chain */
+#define D3D_COLOURED  1   /* colour classes (y mod fh, x mod fw): disjoint windows per launch */
+
+/* variance kinds for d3d_set_problem */
+#define D3D_VAR_SCALAR 0  /* var[n_cubes]            (lib/run.py:186-192 default path) */
+#define D3D_VAR_CUBE   1  /* var[n_cubes][D][H][W]   (lib/run.py:171-184)              */
+
+/* error codes */
+#define D3D_OK          0
+#define D3D_EINVAL     -1  /* bad argument (maps to ValueError / AssertionError)       */
+#define D3D_ECUDA      -2  /* CUDA runtime error                                        */
+#define D3D_ESTATE     -3  /* call order violated (e.g. sweep before set_problem)       */
+#define D3D_ENUMERIC   -4  /* NaN reached the truncated-normal sampler (the reference
+                              raises ValueError at lib/rtnorm.py:144) or a rejection
+                              loop exceeded its guard                                   */
+#define D3D_ENOMEM     -5  /* device allocation failed (MemoryError, lib/run.py:273)    */
+
+typedef struct d3d_ctx d3d_ctx;
+
+/* ---- life cycle ----------------------------------------------------------- */
+int d3d_abi_version(void);
+const char* d3d_last_error(void);
+int d3d_ctx_create(d3d_ctx** out, int device, int dtype);
+int d3d_ctx_destroy(d3d_ctx* ctx);
+/* Run all work of this context on an existing cudaStream_t (e.g. torch's
+ * current stream, so that torch.cuda.Event brackets the kernels). NULL = the
+ * context's own stream (default). */
+int d3d_ctx_set_stream(d3d_ctx* ctx, void* cuda_stream);
+int d3d_ctx_synchronize(d3d_ctx* ctx);
+
+/* ---- problem set-up --------------------------------------------------------
+ * Replaces the state built by Run.__init__ at lib/run.py:139-288: data cube(s),
+ * variance (-> stored as 1/variance), spatial mask (-> row-major site list,
+ * lib/run.py:553-566), FSF image and LSF vector (lib/run.py:208-211; lsf may be
+ * NULL = no spectral convolution, lib/run.py:675-676), parameter boundaries
+ * (lib/line_models.py:76-90), Cauchy jump amplitudes (lib/run.py:251-262) and
+ * the Gibbs a-priori variance (lib/run.py:264-265).
+ *   n_cubes            independent cubes ("galaxies"); each has chains_per_cube chains
+ *   mask               uint8 [n_cubes][H][W] (1 = iterate), or NULL = all ones
+ *   pmin, pmax         [n_cubes][3];   gibbs_prior_var [n_cubes];   jump_amp [3]
+ * The reference's H*W full-cube `contributions` array (lib/run.py:285-288) is
+ * not materialised: each contribution is rank-1 and recomputed from (a,c,w). */
+int d3d_set_problem(d3d_ctx* ctx, int n_cubes, int chains_per_cube,
+                    int D, int H, int W,
+                    const double* data, const double* var, int var_kind,
+                    const uint8_t* mask,
+                    const double* fsf, int fh, int fw,
+                    const double* lsf,
+                    const double* pmin, const double* pmax,
+                    const double* jump_amp, const double* gibbs_prior_var);
+
+/* Truncated-normal tables of lib/rtnorm.py:227,1230,2233 (x[4002], yu[4001],
+ * ncell[8961]); built on the host by deconv3d_b200/rtnorm_tables.py. */
+int d3d_set_rtnorm_tables(d3d_ctx* ctx, const double* x, int nx,
+                          const double* yu, int nyu, const int32_t* ncell, int nncell);
+
+/* Counter-based random stream ("d3d stream v1", Philox4x32-10): replaces the
+ * global numpy.random state of lib/run.py:313,435,578 and lib/rtnorm.py:17.
+ * Chain k of the context draws from (seed, first_chain_id + k). */
+int d3d_set_rng(d3d_ctx* ctx, uint64_t seed, uint32_t first_chain_id);
+
+/* ---- chain state -----------------------------------------------------------
+ * params: [n_chains][H][W][3] float64, n_chains = n_cubes*chains_per_cube,
+ * chain k belongs to cube k / chains_per_cube.  set_params replaces
+ * `self.chain[0] = initial_parameters` (lib/run.py:294-307);
+ * d3d_init_params_uniform the random initialisation of lib/run.py:308-314
+ * (sweep 0 of the stream).  Neither computes the residual: call d3d_forward. */
+int d3d_set_params(d3d_ctx* ctx, const double* params);
+int d3d_get_params(d3d_ctx* ctx, double* params);
+int d3d_init_params_uniform(d3d_ctx* ctx);
+
+/* ---- forward model ---------------------------------------------------------
+ * Replaces Run._compute_error_in_one_step (lib/run.py:999-1031) and
+ * Run.simulate_convolved (lib/run.py:623-652): per-spaxel Gaussian line
+ * (lib/line_models.py:98-109) -> spectral convolution with the LSF with the
+ * exact wrap-around of lib/convolution.py:89-160 -> 2-D true convolution with
+ * the FSF, zero 'same' borders, sources at masked spaxels only.
+ *   sim_out   [n_chains][D][H][W] float64 or NULL
+ *   write_err non-zero: residual <- data - sim (lib/run.py:334, 525-534)
+ *   chi2_out  [n_chains] float64 or NULL: 0.5*sum(err^2/var) over the cube     */
+int d3d_forward(d3d_ctx* ctx, double* sim_out, int write_err, double* chi2_out);
+/* Same, for explicit parameters that are not the chain state (used by
+ * Run.simulate_convolved(shape, parameters)); never touches the residual. */
+int d3d_simulate(d3d_ctx* ctx, const double* params, double* sim_out);
+/* Un-convolved lines, Run.simulate_clean (lib/run.py:597-621). */
+int d3d_simulate_clean(d3d_ctx* ctx, const double* params, double* sim_out);
+/* Current residual err_old as [n_chains][D][H][W] float64 (lib/run.py:334). */
+int d3d_get_residual(d3d_ctx* ctx, double* err_out);
+
+/* Spectral convolution alone: replaces convolve_1d(line, lsf)
+ * (lib/convolution.py:89-120), batch lines of length n, same wrap rule. */
+int d3d_conv1d(d3d_ctx* ctx, const double* lines, int n, int batch,
+               const double* lsf, double* out);
+
+/* Batched truncated normal: replaces rtnorm(a, b, mu, sigma) (lib/rtnorm.py:21-92).
+ * Variate i is drawn from the stream (seed, chain, sweep, site = i), draw index 0
+ * onwards; used_out[i] (may be NULL) receives the number of uniform draws consumed. */
+int d3d_rtnorm(d3d_ctx* ctx, int n, const double* a, const double* b, const double* mu,
+               const double* sigma, uint64_t seed, uint32_t chain, uint32_t sweep,
+               double* out, int32_t* used_out);
+
+/* ---- one proposal, no state change ----------------------------------------
+ * Replaces lib/run.py:391-426 for a given proposal: out[0] = delta =
+ * ar_old - ar_new (the value stored in `likelihoods`, lib/run.py:426-432),
+ * out[1] = ar_old, out[2] = ar_new (windowed 0.5*nansum(err^2/var)). */
+int d3d_delta_logl(d3d_ctx* ctx, int chain, int y, int x,
+                   const double p_new[3], double out[3]);
+
+/* ---- the MH-within-Gibbs sweep --------------------------------------------
+ * Replaces the hot loop lib/run.py:344-537 for iterations
+ * [first_iteration, first_iteration + n_iterations) (the reference's
+ * cur_iteration; the first sweep is iteration 1).  Per site: Cauchy proposal
+ * (:570-579), bounds (:379-388), delta-logL on the FSF window (:400-426),
+ * accept test (:435-451), Gibbs amplitude draw from the truncated normal
+ * (:456-519) and residual update.  The residual refresh of :525-534 happens
+ * inside the call whenever cur_iteration % refresh_every == 0 (0 = never).
+ * Each chain stops by itself when its acceptance rate falls to
+ * min_acceptance_rate (:344-350, 356-359).
+ *   chain_out [n_chains][n_rows][H][W][3], lik_out [n_chains][n_rows][H][W]
+ *             (float64, host or device, NULL = not recorded): row
+ *             it / keep_one_in is written when it % keep_one_in == 0 (:353,:430-451)
+ *   accepted_out  [n_chains] int64: running accepted_count (:341,:440)
+ *   iterations_out[n_chains] int64: value of cur_iteration when the chain stopped
+ *   elapsed_ms    device time of the sweep kernels (CUDA events), or NULL     */
+int d3d_sweep(d3d_ctx* ctx, int64_t first_iteration, int64_t n_iterations,
+              int mode, int keep_one_in, int refresh_every,
+              double min_acceptance_rate,
+              double* chain_out, double* lik_out, int64_t n_rows,
+              int64_t* accepted_out, int64_t* iterations_out, float* elapsed_ms);
+
+/* Introspection for benches: launches of library kernels so far, algorithmic
+ * bytes of the last d3d_sweep (3*s*D*wh*ww per site update with a variance
+ * cube, 2*s*D*wh*ww with a scalar variance), site updates done. */
+int d3d_get_counters(d3d_ctx* ctx, int64_t* kernel_launches,
+                     int64_t* last_sweep_bytes, int64_t* last_sweep_site_updates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECONV3D_B200_H */

@@ -1,0 +1,387 @@
+"""
+GPU parity tests (run with ``-m gpu`` on a B200): the CUDA path, called through
+the C ABI (deconv3d_b200._native / the ``Run`` drop-in), against the CPU oracle
+on the same seeded inputs and against the golden vectors made by the
+reference's own code.
+
+Tolerances (BASELINE.json north_star): convolved cubes 1e-12 relative (fp64) /
+1e-5 (fp32); per-proposal delta-logL 1e-6 relative; identical accept/reject
+decisions in sequential-exact mode given the same uniform stream.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nat():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail('these tests need a CUDA device (there is no CPU fallback)')
+    from deconv3d_b200 import _native
+    return _native
+
+
+def _oracle():
+    from oracle import reference_port, streams, rtnorm_port
+    return reference_port, streams, rtnorm_port
+
+
+def _tables():
+    from deconv3d_b200 import rtnorm_tables
+    x, yu, nc = rtnorm_tables.tables()
+    return x, yu, nc.astype(np.int64)
+
+
+def synthetic(D, H, W, seed, noise=0.05):
+    rs = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:H, 0:W]
+    a = 8.0 * np.exp(-((yy - H / 2.) ** 2 + (xx - W / 2.) ** 2) / (2. * (0.35 * H) ** 2))
+    c = D / 2. + 0.15 * D * np.tanh((xx - W / 2.) / (0.3 * W))
+    w = 1.2 + 0.05 * yy
+    z = np.arange(D)[:, None, None]
+    return a * np.exp(-(z - c) ** 2 / (2 * w ** 2)) + noise * rs.randn(D, H, W)
+
+
+def make_ctx(nat, data, var, fsf, lsf, mask=None, dtype=None, chains=1, seed=42, first_chain=0,
+             jump=(0.0, 0.1, 0.1), prior=None):
+    port, _, _ = _oracle()
+    pmin, pmax = port.single_gaussian_boundaries(data, fsf)
+    ctx = nat.Context(0, nat.F64 if dtype is None else dtype)
+    ctx.set_rtnorm_tables(*_tables())
+    ctx.set_rng(seed, first_chain)
+    if prior is None:
+        prior = float(pmax[0]) ** 2
+    ctx.set_problem(data, var, fsf, lsf, pmin, pmax, jump, prior, mask=mask,
+                    chains_per_cube=chains)
+    return ctx, np.array(pmin, float), np.array(pmax, float)
+
+
+# ---------------------------------------------------------------------------
+def test_conv1d_vs_reference_golden(nat):
+    g = load_golden('ref_conv1d')
+    ctx = nat.Context(0, nat.F64)
+    for D in (2, 3, 8, 16, 21, 30, 31, 32, 33, 40, 41, 63, 64, 65):
+        out = ctx.conv1d(g['line_%d' % D], g['lsf_%d' % D])
+        np.testing.assert_allclose(out, g['out_%d' % D], rtol=1e-12, atol=1e-15)
+        out = ctx.conv1d(g['line_%d' % D], g['lsfrand_%d' % D])
+        np.testing.assert_allclose(out, g['outrand_%d' % D], rtol=1e-12, atol=1e-14)
+    # batched + the drop-in function with the reference's (conv, fftpsf) protocol
+    from deconv3d_b200 import convolve_1d
+    rs = np.random.RandomState(0)
+    lines = rs.rand(5, 7, 30)
+    lsf = g['lsf_30']
+    out, fftpsf = convolve_1d(lines, lsf, axis=2)
+    port, _, _ = _oracle()
+    for i in range(5):
+        for j in range(7):
+            np.testing.assert_allclose(out[i, j], port.convolve_1d(lines[i, j], lsf)[0],
+                                       rtol=1e-12, atol=1e-15)
+    out2, _ = convolve_1d(lines[0, 0], fftpsf, compute_fourier=False)
+    np.testing.assert_allclose(out2, out[0, 0], rtol=1e-12, atol=1e-15)
+    assert np.allclose(fftpsf, port.convolve_1d(lines[0, 0], lsf)[1])
+
+
+def test_rtnorm_vs_reference_golden(nat):
+    g = load_golden('ref_rtnorm')
+    ctx = nat.Context(0, nat.F64)
+    ctx.set_rtnorm_tables(*_tables())
+    c = g['cases']
+    out, used = ctx.rtnorm_batch(c[:, 0], c[:, 1], c[:, 2], c[:, 3], seed=int(g['seed']),
+                                 chain=int(g['chain']), sweep=int(g['sweep']))
+    assert np.array_equal(used, g['used'])               # same branch, same number of draws
+    np.testing.assert_allclose(out, g['out'], rtol=1e-9, atol=1e-9)
+    assert np.all(out >= c[:, 0]) and np.all(out <= c[:, 1])
+
+
+def test_rtnorm_moments(nat):
+    from deconv3d_b200 import rtnorm
+    r = rtnorm(1., 17., mu=7., sigma=5., size=200000, seed=5)     # tests/rtnorm_test.py:16-34
+    assert r.min() >= 1. and r.max() <= 17.
+    from scipy.stats import truncnorm
+    tn = truncnorm((1. - 7.) / 5., (17. - 7.) / 5., loc=7., scale=5.)
+    assert abs(r.mean() - tn.mean()) < 0.05
+    assert abs(r.std() - tn.std()) < 0.05
+    r = rtnorm(0, 2 ** 63 - 1, size=42, seed=1)                    # tests/rtnorm_test.py:36-56
+    assert isinstance(r, np.ndarray) and len(r) == 42 and (r > 0).all()
+    with pytest.raises(Exception):
+        rtnorm(2., 1.)
+
+
+@pytest.mark.parametrize('dtype_name,rtol', [('f64', 1e-12), ('f32', 1e-5)])
+def test_forward_mat_known_answer(nat, dtype_name, rtol):
+    port, _, _ = _oracle()
+    g = load_golden('mat_kat')
+    data, var, fsf, params = g['data'], g['variance'], g['fsf'], g['params']
+    delta = port.gaussian_lsf_vector(0.0, 1.25e-4, data.shape[0])
+    ctx, _, _ = make_ctx(nat, data, var, fsf, delta,
+                         dtype=nat.F64 if dtype_name == 'f64' else nat.F32)
+    ctx.set_params(params[None])
+    sim, chi2 = ctx.forward(want_sim=True, write_err=True, want_chi2=True)
+    mask = np.ones(data.shape[1:])
+    err_ref = port.compute_error_in_one_step(data, params, fsf, delta, mask)
+    scale = np.abs(data - err_ref).max()
+    np.testing.assert_allclose(sim[0], data - err_ref, rtol=1e-12, atol=1e-12 * scale)
+    np.testing.assert_allclose(ctx.get_residual()[0], err_ref, rtol=rtol,
+                               atol=rtol * np.abs(data).max())
+    chi2_ref = 0.5 * np.sum(err_ref ** 2 / var)
+    assert abs(chi2[0] - chi2_ref) <= max(rtol, 1e-10) * chi2_ref * 10
+    assert abs(2 * chi2[0] / data.size - 0.999) < 2e-3
+
+
+@pytest.mark.parametrize('shape,fsf_kind,lsf_fwhm', [
+    ((30, 11, 12), 'gauss13', 0.0002675),      # D=30: spectral wrap
+    ((32, 9, 9), 'moffat7', 0.0004),           # P=32 full wrap
+    ((40, 16, 14), 'ell9', 0.0002675),
+    ((21, 8, 15), 'rect5x9', None),            # no LSF (lib/run.py:675-676), non-square FSF
+    ((64, 6, 7), 'gauss13', 0.0006),
+])
+def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
+    port, _, _ = _oracle()
+    D, H, W = shape
+    rs = np.random.RandomState(D + H)
+    step = 0.2
+    fsf = {
+        'gauss13': lambda: port.gaussian_fsf_image(1.0, step),
+        'moffat7': lambda: port.moffat_fsf_image((7, 7), step, fwhm_arcsec=0.8, beta=2.5),
+        'ell9': lambda: port.gaussian_fsf_image(0.6, step, pa=30., ba=0.7),
+        'rect5x9': lambda: (lambda f: f / f.sum())(rs.rand(5, 9)),
+    }[fsf_kind]()
+    lsf = None if lsf_fwhm is None else port.gaussian_lsf_vector(lsf_fwhm, 1.25e-4, D)
+    data = synthetic(D, H, W, 3)
+    mask = (rs.rand(H, W) > 0.2).astype(float)
+    params = np.dstack([rs.rand(H, W) * 9, rs.rand(H, W) * (D - 1), 0.3 + rs.rand(H, W) * 4])
+    ctx, _, _ = make_ctx(nat, data, np.array([0.01]), fsf, lsf, mask=mask)
+    ctx.set_params(params[None])
+    sim, _ = ctx.forward(want_sim=True, write_err=True)
+    err_ref = port.compute_error_in_one_step(data, params, fsf, lsf, mask)
+    sim_ref = data - err_ref
+    np.testing.assert_allclose(sim[0], sim_ref, rtol=1e-12, atol=1e-12 * np.abs(sim_ref).max())
+    np.testing.assert_allclose(ctx.get_residual()[0], err_ref, rtol=1e-12,
+                               atol=1e-12 * np.abs(data).max())
+    # simulate_clean / simulate with explicit parameters
+    np.testing.assert_allclose(ctx.simulate(params[None])[0], sim_ref, rtol=1e-12,
+                               atol=1e-12 * np.abs(sim_ref).max())
+    np.testing.assert_allclose(ctx.simulate_clean(params[None])[0],
+                               port.simulate_clean(data.shape, params, mask),
+                               rtol=1e-13, atol=1e-300)
+
+
+@pytest.mark.parametrize('var_kind', ['scalar', 'cube'])
+def test_delta_logl_vs_oracle(nat, var_kind):
+    """Per-proposal (delta, ar_old, ar_new) against the reference's windowed sums
+    (lib/run.py:400-426) on the same residual."""
+    port, _, _ = _oracle()
+    D, H, W = 30, 12, 13
+    rs = np.random.RandomState(8)
+    data = synthetic(D, H, W, 5)
+    fsf = port.gaussian_fsf_image(0.7, 0.2)                     # 9x9
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    var = np.array([0.05 ** 2]) if var_kind == 'scalar' else 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    var_cube = np.ones((D, H, W)) * var if var_kind == 'scalar' else var
+    mask = np.ones((H, W))
+    params = np.dstack([rs.rand(H, W) * 9, 5 + rs.rand(H, W) * 20, 0.8 + rs.rand(H, W) * 3])
+    ctx, _, _ = make_ctx(nat, data, var, fsf, lsf)
+    ctx.set_params(params[None])
+    ctx.forward(write_err=True)
+    err_old = port.compute_error_in_one_step(data, params, fsf, lsf, mask)
+    fhh = (fsf.shape[0] - 1) // 2
+    for (y, x) in [(0, 0), (5, 6), (11, 12), (3, 12), (11, 0), (6, 1)]:
+        for trial in range(3):
+            p_new = params[y, x].copy()
+            p_new[1] += 0.3 * rs.randn()
+            p_new[2] += 0.2 * rs.randn()
+            if trial == 2:
+                p_new[0] *= 1.1                                  # amplitude may move too
+            c_old, _ = port.contribution_of_spaxel(x, y, params[y, x], W, H, D, fsf, lsf)
+            c_new, _ = port.contribution_of_spaxel(x, y, p_new, W, H, D, fsf, lsf)
+            err_new = (err_old + c_old) - c_new
+            sl = (slice(None), slice(max(y - fhh, 0), min(y + fhh + 1, H)),
+                  slice(max(x - fhh, 0), min(x + fhh + 1, W)))
+            ar_old = 0.5 * np.nansum(err_old[sl] ** 2 / var_cube[sl])
+            ar_new = 0.5 * np.nansum(err_new[sl] ** 2 / var_cube[sl])
+            out = ctx.delta_logl(0, y, x, p_new)
+            delta = ar_old - ar_new
+            # the reference value is a difference of two O(N/2) sums: allow its own
+            # cancellation noise on top of the 1e-6 relative bar
+            assert abs(out[0] - delta) <= 1e-6 * abs(delta) + 1e-11 * ar_old, (y, x, out, delta)
+            assert abs(out[1] - ar_old) <= 1e-10 * ar_old
+            assert abs(out[2] - ar_new) <= 1e-10 * ar_new + 1e-11 * ar_old
+
+
+def _compare_chain(nat, data, fsf, lsf, var_in, mask_in, init, max_it, keep, seed, mode='seq',
+                   jump=0.1, prior=None, dtype=None, rtol=1e-9):
+    port, streams, _ = _oracle()
+    tables = _tables()
+    D, H, W = data.shape
+    var_cube = None
+    if var_in is not None:
+        var_cube = var_in if var_in.ndim == 3 else np.ones(data.shape) * var_in[0]
+    trace = {}
+    order = None
+    m_for_order = port.prepare_mask(data, None if mask_in is None else mask_in.copy())
+    if mode == 'colour':
+        order = port.colour_class_order(m_for_order, fsf.shape[0], fsf.shape[1])
+    ref = port.run_chain(data, fsf, lsf, streams.PhiloxStream(seed, 0),
+                         mask=None if mask_in is None else mask_in.copy(),
+                         variance_cube=var_cube, initial_parameters=init,
+                         jump_amplitude=jump, gibbs_apriori_variance=prior,
+                         max_iterations=max_it, keep_one_in=keep, trace=trace,
+                         rtnorm_tables=tables, site_order=order)
+    var_dev = ref['variance_cube'] if var_in is None or var_in.ndim == 3 else var_in
+    if var_in is None:
+        var_dev = np.array([ref['variance_cube'].flat[0]])
+    jump_vec = np.ones(3) * np.array(jump)
+    jump_vec[0] = 0
+    ctx, pmin, pmax = make_ctx(nat, data, var_dev, fsf, lsf, mask=ref['mask'], seed=seed,
+                               jump=jump_vec, prior=ref['gibbs_apriori_variance'], dtype=dtype)
+    n_saved = ref['chain'].shape[0]
+    chain = np.zeros((1, n_saved, H, W, 3))
+    lik = np.zeros((1, n_saved, H, W))
+    if init is not None:
+        ctx.set_params(np.asarray(init, float)[None])
+    else:
+        ctx.init_params_uniform()
+    chain[0, 0] = ctx.get_params()[0]
+    ctx.forward(write_err=True)
+    acc, its, ms = ctx.sweep(1, max_it - 1, mode=nat.SEQ_EXACT if mode == 'seq' else nat.COLOURED,
+                             keep_one_in=keep, chain_out=chain, lik_out=lik)
+    m = ref['mask'] == 1
+    assert its[0] == ref['iterations']
+    # accept / reject decisions: identical, proposal by proposal
+    n_acc_ref = sum(1 for v in trace.values() if v[3])
+    assert acc[0] - m.sum() == n_acc_ref, (acc[0], n_acc_ref)
+    if keep == 1:
+        for it in range(1, max_it):
+            moved = (chain[0, it, :, :, 1] != chain[0, it - 1, :, :, 1]) | \
+                    (chain[0, it, :, :, 2] != chain[0, it - 1, :, :, 2])
+            ref_acc = np.zeros((H, W), bool)
+            for (y, x) in zip(*np.nonzero(m)):
+                ref_acc[y, x] = trace[(it, y, x)][3]
+            assert np.array_equal(moved & m, ref_acc), 'decisions differ at iteration %d' % it
+    np.testing.assert_allclose(chain[0][:, m], ref['chain'][:, m], rtol=rtol, atol=1e-12)
+    np.testing.assert_allclose(lik[0][1:, m], ref['likelihoods'][1:, m], rtol=max(rtol, 1e-6),
+                               atol=1e-9)
+    np.testing.assert_allclose(ctx.get_residual()[0], ref['err'], rtol=0,
+                               atol=1e-9 * np.abs(data).max())
+    return ref, chain, lik
+
+
+def test_seq_exact_small_scalar_variance(nat):
+    """Case A of the goldens: 12x9x10, 7x7 Gaussian FSF, default (scalar) variance,
+    random initial parameters drawn on the device (sweep 0 of the stream)."""
+    g = load_golden('ref_run_A')
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], None, None, None, 25, 1, seed=7)
+
+
+def test_seq_exact_mask_variance_cube_wrap(nat):
+    """Case C: mask, variance cube, initial parameters (one amplitude = 0), keep_one_in,
+    D=16 (full spectral wrap), rotated elliptical FSF, custom jump and Gibbs prior."""
+    g = load_golden('ref_run_C')
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], g['in_variance'], g['in_mask'],
+                   g['in_initial_parameters'], 12, 2, seed=3, jump=0.3, prior=50.0)
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], g['in_variance'], g['in_mask'],
+                   g['in_initial_parameters'], 9, 1, seed=4, jump=0.3, prior=50.0)
+
+
+def test_seq_exact_muse_cube(nat):
+    """cfg1: the bundled MUSE cube x1e20, MUSE() defaults (13x13 FSF, D=30 wrap)."""
+    g = load_golden('ref_run_B')
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], None, None, None, 4, 1, seed=11)
+
+
+def test_seq_exact_crosses_refresh(nat):
+    """> 1000 iterations: the residual refresh of lib/run.py:525-534 happens inside."""
+    g = load_golden('ref_run_D')
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], None, None, None, 1003, 50, seed=13,
+                   rtol=1e-7)
+
+
+def test_coloured_mode_vs_oracle_same_order(nat):
+    g = load_golden('ref_run_A')
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], None, None, None, 12, 1, seed=21,
+                   mode='colour')
+    g = load_golden('ref_run_C')
+    _compare_chain(nat, g['data'], g['fsf'], g['lsf'], g['in_variance'], g['in_mask'],
+                   g['in_initial_parameters'], 8, 1, seed=5, jump=0.3, prior=50.0, mode='colour')
+
+
+def test_fp32_storage_chain_close(nat):
+    """float32 storage: same decisions are not required; the chain must stay close over
+    a few sweeps and the residual must match its own forward model."""
+    g = load_golden('ref_run_A')
+    port, streams, _ = _oracle()
+    ref = port.run_chain(g['data'], g['fsf'], g['lsf'], streams.PhiloxStream(7, 0),
+                         max_iterations=3, rtnorm_tables=_tables())
+    ctx, _, _ = make_ctx(nat, g['data'], np.array([ref['variance_cube'].flat[0]]), g['fsf'],
+                         g['lsf'], seed=7, dtype=nat.F32)
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+    chain = np.zeros((1, 3, 9, 10, 3))
+    ctx.sweep(1, 2, chain_out=chain)
+    np.testing.assert_allclose(chain[0, 1], ref['chain'][1], rtol=2e-3, atol=2e-3)
+    res = ctx.get_residual()[0]
+    ctx.forward(write_err=True)
+    np.testing.assert_allclose(res, ctx.get_residual()[0], rtol=0, atol=1e-4)
+
+
+def test_many_chains_equal_single_chain_runs(nat):
+    """Chain k of a multi-chain context is bit-identical to a single-chain context whose
+    stream is (seed, first_chain_id = k): chains are independent units (no collective)."""
+    g = load_golden('ref_run_A')
+    data, fsf, lsf = g['data'], g['fsf'], g['lsf']
+    var = np.array([0.01])
+    out = []
+    ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=5, seed=99)
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+    chain = np.zeros((5, 6, 9, 10, 3))
+    ctx.sweep(1, 5, chain_out=chain)
+    for k in (0, 3, 4):
+        c1, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=1, seed=99, first_chain=k)
+        c1.init_params_uniform()
+        c1.forward(write_err=True)
+        ch = np.zeros((1, 6, 9, 10, 3))
+        c1.sweep(1, 5, chain_out=ch)
+        ch[0, 0] = c1.get_params()[0] * 0 + ch[0, 0]
+        assert np.array_equal(ch[0, 1:], chain[k, 1:])
+    assert not np.array_equal(chain[0, 1:], chain[1, 1:])
+
+
+def test_multi_cube_galaxies(nat):
+    """Survey-batch layout (cfg5): independent cubes with their own data, variance,
+    mask and boundaries in one context equal the per-cube contexts."""
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(2)
+    fsf = port.gaussian_fsf_image(0.5, 0.2)
+    D, H, W = 16, 8, 9
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    cubes = np.stack([synthetic(D, H, W, s) for s in (1, 2, 3)])
+    var = 0.05 ** 2 * (1 + rs.rand(3, D, H, W))
+    masks = (rs.rand(3, H, W) > 0.3).astype(np.uint8)
+    pmin = np.zeros((3, 3))
+    pmax = np.array([[cubes[i].max() / fsf.max(), D - 1, D] for i in range(3)])
+    prior = pmax[:, 0] ** 2
+    ctx = nat.Context(0, nat.F64)
+    ctx.set_rtnorm_tables(*_tables())
+    ctx.set_rng(5, 0)
+    ctx.set_problem(cubes, var, fsf, lsf, pmin, pmax, [0, 0.1, 0.1], prior, mask=masks,
+                    chains_per_cube=2)
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+    chain = np.zeros((6, 4, H, W, 3))
+    ctx.sweep(1, 3, chain_out=chain)
+    for i in range(3):
+        c1 = nat.Context(0, nat.F64)
+        c1.set_rtnorm_tables(*_tables())
+        c1.set_rng(5, 2 * i)
+        c1.set_problem(cubes[i], var[i], fsf, lsf, pmin[i], pmax[i], [0, 0.1, 0.1], prior[i],
+                       mask=masks[i], chains_per_cube=2)
+        c1.init_params_uniform()
+        c1.forward(write_err=True)
+        ch = np.zeros((2, 4, H, W, 3))
+        c1.sweep(1, 3, chain_out=ch)
+        assert np.array_equal(ch[:, 1:], chain[2 * i:2 * i + 2, 1:])
