@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""
+bench.py -- logL evaluations/s and Gibbs sweeps/s of the deconv3d likelihood hot
+path on B200 (BASELINE.json metric), with roofline, CPU baseline and clocks.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2x256|cfg2|cfg1|cfg5] [--mode sequential|coloured]
+                    [--chains C] [--sweeps S] [--dtype f64|f32]
+
+One "step" = S Gibbs sweeps (default 20) of every chain on the GPU: for each masked
+spaxel of each chain one proposal + delta-logL evaluation + accept test + Gibbs
+amplitude draw + residual update.  value = logL evaluations (= site updates) per
+second summed over all ranks, inputs resident in HBM; e2e = the same metric through
+the public ``Run(...)`` API with host (numpy) buffers in and chain rows out.
+
+For N > 1 launch under torchrun (one rank per GPU); chains are sharded by rank, there
+is no collective in the sweep (scaling: weak).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'logL evals/s'
+UNIT = 'evals/s'
+
+
+# ----------------------------------------------------------------------------------
+def build_workload(name, chains):
+    """Returns dict(data [n,D,H,W] builder inputs...) describing the workload on the host."""
+    from deconv3d_b200 import synthetic
+    if name in ('cfg2', 'cfg2x256'):
+        D = H = W = 40
+        inst = synthetic.muse_wfm_instrument('moffat', 13)
+        truth = synthetic.halpha_truth(D, H, W)
+        return dict(name=name, D=D, H=H, W=W, inst=inst, truth=truth[None], n_cubes=1,
+                    chains_per_cube=chains, var_kind='cube', sigma=0.05,
+                    desc='synthetic MUSE WFM Halpha cube 40x40x40, Moffat FWHM 0.8" beta 2.5 '
+                         '13x13, MUSE LSF, variance cube 0.05^2, %d chain(s)/GPU' % chains)
+    if name == 'cfg5':
+        D = H = W = 32
+        inst = synthetic.muse_wfm_instrument('moffat', 11)
+        rs = np.random.RandomState(5)
+        truth = np.stack([synthetic.halpha_truth(D, H, W) * np.array([0.5 + rs.rand(), 1.0, 1.0])
+                          for _ in range(chains)])
+        return dict(name=name, D=D, H=H, W=W, inst=inst, truth=truth, n_cubes=chains,
+                    chains_per_cube=1, var_kind='cube', sigma=0.05,
+                    desc='survey batch: %d independent synthetic galaxies 32x32x32 per GPU, '
+                         'FSF 11x11, per-galaxy data + variance' % chains)
+    if name == 'cfg1':
+        data = np.load(os.path.join(ROOT, 'tests', 'golden', 'muse_cube_01.npz'))['data'] * 1e20
+        from deconv3d_b200 import MUSE
+        return dict(name=name, D=30, H=30, W=30, inst=MUSE(), data=data[None], n_cubes=1,
+                    chains_per_cube=chains, var_kind='scalar',
+                    desc='bundled MUSE test cube 30x30x30 x1e20, MUSE() defaults (Gaussian FSF '
+                         '13x13), scalar variance, %d chain(s)/GPU' % chains)
+    raise SystemExit('unknown workload %s' % name)
+
+
+def realise(wl, rank):
+    """Host arrays of the workload: data, variance, fsf, lsf, boundaries."""
+    from deconv3d_b200 import _native, MUSE
+    from deconv3d_b200.math_utils import median_clip
+    D, H, W = wl['D'], wl['H'], wl['W']
+    cube0 = MUSE().build_cube(np.zeros((D, H, W)))
+    fsf = np.asarray(wl['inst'].fsf.as_image(cube0), dtype=np.float64)
+    lsf = wl['inst'].lsf.as_vector(cube0)
+    if 'data' in wl:
+        data = wl['data']
+    else:
+        # noiseless cube from the product's own forward model, then Gaussian noise
+        n = wl['n_cubes']
+        ctx = _native.Context(0 if 'LOCAL_RANK' not in os.environ else int(os.environ['LOCAL_RANK']))
+        pmax = np.array([[100., D - 1, D]] * n)
+        ctx.set_problem(np.ones((n, D, H, W)), np.ones(n), fsf, lsf, np.zeros((n, 3)), pmax,
+                        [0, .1, .1], np.ones(n))
+        clean = ctx.simulate(wl['truth'])
+        ctx.close()
+        from deconv3d_b200 import synthetic
+        data = clean + synthetic.noise(clean.shape, wl['sigma'], 1234 + rank)
+    n = data.shape[0]
+    if wl['var_kind'] == 'cube':
+        var = np.full(data.shape, wl['sigma'] ** 2)
+    else:
+        var = np.zeros(n)
+        for i in range(n):
+            _, s, _ = median_clip(np.copy(data[i][2:-2, 2:-4, 2:4]), 2.5)
+            var[i] = (s if s != 0 else 1e-20) ** 2
+    pmin = np.zeros((n, 3))
+    pmax = np.array([[data[i].max() / fsf.max(), D - 1, D] for i in range(n)])
+    return dict(data=data, var=var, fsf=fsf, lsf=lsf, pmin=pmin, pmax=pmax,
+                prior=pmax[:, 0] ** 2)
+
+
+# ----------------------------------------------------------------------------------
+class ClockSampler(object):
+    """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(',')])
+            except Exception:           # noqa: BLE001
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names)
+                   if any(s[3 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(self.samples[0][1]),
+                'reasons': reasons, 'samples': len(self.samples),
+                'power_w_max': max(float(s[2]) for s in self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:               # noqa: BLE001
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ----------------------------------------------------------------------------------
+def cpu_reference(wl_name, sweeps, n_procs, sample_sites=None):
+    """The reference's CPU path (oracle literal port, lib/run.py:344-519 incl. the
+    full-cube temporaries and numpy-FFT spectral convolution) on the same workload;
+    n_procs independent chains, one per process."""
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    with ctx.Pool(n_procs) as pool:
+        res = pool.map(_cpu_chain, [(wl_name, sweeps, k) for k in range(n_procs)])
+    wall = max(r[0] for r in res)
+    updates = sum(r[1] for r in res)
+    return updates / wall, wall, updates
+
+
+def _cpu_chain(args):
+    wl_name, sweeps, k = args
+    os.environ['OMP_NUM_THREADS'] = '1'
+    from oracle import reference_port as port, streams
+    from deconv3d_b200 import synthetic, MUSE
+    # the same cube family as the GPU arm, built on the CPU by the oracle's forward model
+    if wl_name in ('cfg2', 'cfg2x256'):
+        D = H = W = 40
+        inst = synthetic.muse_wfm_instrument('moffat', 13)
+        truth = synthetic.halpha_truth(D, H, W)
+    elif wl_name == 'cfg5':
+        D = H = W = 32
+        inst = synthetic.muse_wfm_instrument('moffat', 11)
+        truth = synthetic.halpha_truth(D, H, W)
+    else:
+        D = H = W = 30
+        inst = MUSE()
+        truth = None
+    cube0 = MUSE().build_cube(np.zeros((D, H, W)))
+    fsf = np.asarray(inst.fsf.as_image(cube0))
+    lsf = inst.lsf.as_vector(cube0)
+    mask = np.ones((H, W))
+    if truth is None:
+        data = np.load(os.path.join(ROOT, 'tests', 'golden', 'muse_cube_01.npz'))['data'] * 1e20
+        var = None
+    else:
+        data = -port.compute_error_in_one_step(np.zeros((D, H, W)), truth, fsf, lsf, mask) \
+            + synthetic.noise((D, H, W), 0.05, 1234)
+        var = np.full(data.shape, 0.05 ** 2)
+    st = streams.PhiloxStream(42, k)
+    # warm-up sweep excluded from the timing: run 2 iterations first (1 sweep)
+    t0 = time.perf_counter()
+    port.run_chain(data, fsf, lsf, st, variance_cube=var, max_iterations=2, refresh_every=0)
+    t_setup = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    port.run_chain(data, fsf, lsf, st, variance_cube=var, max_iterations=sweeps + 1,
+                   refresh_every=0)
+    t_all = time.perf_counter() - t0
+    # both calls pay the same initial simulation; the difference is (sweeps-1) sweeps
+    dt = max(t_all - t_setup, 1e-9)
+    return dt, (sweeps - 1) * H * W
+
+
+# ----------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2x256', choices=['cfg2x256', 'cfg2', 'cfg1', 'cfg5'])
+    ap.add_argument('--mode', default='sequential', choices=['sequential', 'coloured'])
+    ap.add_argument('--chains', type=int, default=None, help='chains (or galaxies) per GPU')
+    ap.add_argument('--sweeps', type=int, default=None, help='Gibbs sweeps per step')
+    ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--cpu-sweeps', type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    chains = args.chains if args.chains is not None else \
+        {'cfg2x256': 256, 'cfg2': 1, 'cfg1': 1, 'cfg5': 512}[args.workload]
+    sweeps = args.sweeps if args.sweeps is not None else \
+        {'cfg2x256': 20, 'cfg2': 200, 'cfg1': 200, 'cfg5': 20}[args.workload]
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        n_procs = os.cpu_count() or 1
+        cs = args.cpu_sweeps or 3
+        per_step = []
+        for _ in range(max(args.warmup, 0) and 1):
+            cpu_reference(args.workload, 2, n_procs)
+        for _ in range(args.steps):
+            v, wall, upd = cpu_reference(args.workload, cs, n_procs)
+            per_step.append((v, wall))
+        v = float(np.mean([p[0] for p in per_step]))
+        wl = build_workload(args.workload, chains)
+        line = {
+            'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * float(np.mean([p[1] for p in per_step])),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': {'workload': wl['desc'], 'mode': 'sequential (reference order)'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': n_procs, 'kind': 'port',
+                             'sample': '%d independent chains (one process per host core), %d timed '
+                                       'sweeps each, oracle literal numpy/FFT path' % (n_procs, cs - 1)},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'sweeps_per_s': v / (wl['H'] * wl['W']),
+        }
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: deconv3d_b200 has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    from deconv3d_b200 import _native, rtnorm_tables
+    wl = build_workload(args.workload, chains)
+    arrays = realise(wl, rank)
+    D, H, W = wl['D'], wl['H'], wl['W']
+    n_sites = H * W
+    n_chains = wl['n_cubes'] * wl['chains_per_cube']
+    mode = _native.SEQ_EXACT if args.mode == 'sequential' else _native.COLOURED
+
+    ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_rtnorm_tables(*rtnorm_tables.tables())
+    ctx.set_rng(42, rank * n_chains)
+    ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                    arrays['pmax'], [0, 0.1, 0.1], arrays['prior'],
+                    chains_per_cube=wl['chains_per_cube'])
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    it = 1
+    for _ in range(args.warmup):
+        ctx.sweep(it, sweeps, mode=mode, refresh_every=1000, min_acceptance_rate=0.0)
+        it += sweeps
+    launches0 = ctx.counters()['kernel_launches']
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_ms, kern_ms, bytes_algo, updates = [], [], 0, 0
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            flush.fill_(1)                       # L2 flush between timed iterations
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _, _, ms = ctx.sweep(it, sweeps, mode=mode, refresh_every=1000,
+                                 min_acceptance_rate=0.0)
+            e1.record(stream)
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            kern_ms.append(ms)
+            c = ctx.counters()
+            bytes_algo += c['last_sweep_bytes']
+            updates += c['last_sweep_site_updates']
+            it += sweeps
+        barrier()
+    launches = ctx.counters()['kernel_launches'] - launches0
+    total_ms = float(np.sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device='cuda')
+    u = torch.tensor([float(updates)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    total_ms_max, updates_all = float(t.item()), float(u.item())
+    value = updates_all / (total_ms_max * 1e-3)
+
+    # ---- end-to-end through the public API: host buffers in, chain rows out -------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, arrays, rank, local_rank, world, sweeps)
+
+    if world > 1 and rank != 0:
+        dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    kern_total_ms = float(np.sum(kern_ms))
+    achieved = bytes_algo / (kern_total_ms * 1e-3) / 1e9
+    state_mb = n_chains * D * H * W * (8 if args.dtype == 'f64' else 4) / 1e6
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'mode': args.mode, 'sweeps_per_step': sweeps,
+                   'chains_per_gpu': n_chains, 'sites_per_sweep': n_sites,
+                   'residual_state_MB_per_gpu': state_mb,
+                   'l2': 'explicit 256 MiB L2 flush between timed steps'},
+        'sweeps_per_s': value / n_sites,
+        'gpu_launches': int(launches),
+        'clocks': clocks.summary(),
+        'roofline': {
+            'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+            'kernel': 'sweep_seq_kernel' if args.mode == 'sequential' else 'sweep_colour_kernel',
+            'algorithmic_bytes_per_launch': bytes_algo / max(1, args.steps),
+            'kernel_ms_per_launch': kern_total_ms / max(1, args.steps),
+            'note': 'algorithmic bytes = (3 with a variance cube | 2 with a scalar variance) * s * D * '
+                    'sum_sites wh*ww per chain per sweep (SURVEY.md 8d); consecutive windows of a '
+                    'chain overlap, so cache hits can push this above the HBM peak',
+        },
+    }
+    if e2e is not None:
+        line['e2e'] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        cs = args.cpu_sweeps or 3
+        n_procs = min(os.cpu_count() or 1, 8)
+        v, wall, upd = cpu_reference(args.workload, cs, 1)
+        line['cpu_baseline'] = {
+            'value': v, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': '1 chain, %d timed sweeps (%d site updates) of the same cube on one host core '
+                      '(numpy is single-threaded on this path); host has %d cores'
+                      % (cs - 1, upd, os.cpu_count() or 1)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, wl, arrays, rank, local_rank, world, sweeps):
+    """Same metric through ``Run(...)``: numpy cube/variance in, chain rows out."""
+    import torch
+    import torch.distributed as dist
+    from deconv3d_b200 import Run, MUSE
+    if wl['n_cubes'] != 1:
+        return None
+    cube = MUSE().build_cube(arrays['data'][0])
+    var = arrays['var'][0] if wl['var_kind'] == 'cube' else None
+    chains = wl['chains_per_cube']
+    keep = max(1, sweeps // 2)
+    kw = dict(variance=var, max_iterations=sweeps + 1, keep_one_in=keep, n_chains=chains,
+              seed=42, first_chain_id=rank * chains, device=local_rank,
+              mode=args.mode, dtype='float64' if args.dtype == 'f64' else 'float32',
+              min_acceptance_rate=0.0)
+    import logging
+    logging.getLogger('deconv3d').setLevel(logging.WARNING)
+    Run(cube, wl['inst'], **kw)                       # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run = Run(cube, wl['inst'], **kw)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    updates = sweeps * wl['H'] * wl['W'] * chains * world
+    h2d = arrays['data'][0].nbytes + (var.nbytes if var is not None else 8) + arrays['fsf'].nbytes \
+        + arrays['lsf'].nbytes
+    d2h = run.chains[:, 1:].nbytes + run.all_likelihoods[:, 1:].nbytes + run.chains[:, 0].nbytes
+    return {'value': updates / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+            'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
+            'api': 'Run(cube, instrument, variance=..., max_iterations=%d, keep_one_in=%d, '
+                   'n_chains=%d)' % (sweeps + 1, keep, chains)}
+
+
+if __name__ == '__main__':
+    main()

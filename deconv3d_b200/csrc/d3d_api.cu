@@ -12,6 +12,7 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <stdlib.h>
 
 #include "../../include/deconv3d_b200.h"
 #include "d3d_kernels.cuh"
@@ -50,7 +51,9 @@ struct d3d_ctx {
     std::vector<void*> allocs;          // problem-lifetime allocations
     void* rt_x = nullptr; void* rt_yu = nullptr; void* rt_nc = nullptr;
     double* d_lines = nullptr;          // [n_chains][H][W][Dp] scratch of the forward model
-    int threads = 256, ne = 0;          // sweep launch configuration
+    int threads = 256, ne = 0;          // sweep launch configuration (row-mapped kernels)
+    int generic_threads = 256;
+    bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
     int64_t window_voxels_per_sweep = 0;   // sum over cubes of sum_sites wh*ww*D * chains_per_cube
@@ -156,21 +159,25 @@ static int ingest(d3d_ctx* c, const double* src_any, const double* nan_src_dev, 
 }
 
 static void choose_launch(d3d_ctx* c) {
+    // Row-mapped kernels: fw * (Dp/VEC) window threads (<= 512) + 2 scalar warps, the window
+    // rows (<= fh) cached in registers: NE in {7, 13, 21}.  Anything bigger: generic kernels.
     const Problem& pb = c->pb;
     const int vec = c->dtype == D3D_F64 ? 2 : 4;
     const int zl = pb.Dp / vec;
-    const int npos = pb.fh * pb.fw;
-    int best_threads = 256, best_ne = 0;
-    for (int threads = 256; threads <= 512; threads *= 2) {
-        int t = std::max(threads, ((std::max(pb.Dp, zl) + 31) / 32) * 32);
-        if (t > 1024) break;
-        int nc = std::max(1, t / zl);
-        int need = (npos + nc - 1) / nc;
-        if (need <= 16) { best_threads = t; best_ne = need <= 4 ? 4 : need <= 8 ? 8 : 16; break; }
-        best_threads = std::max(256, ((std::max(pb.Dp, zl) + 31) / 32) * 32);
+    const int nwt = pb.fw * zl;
+    c->ne = 0;
+    c->threads = 256;
+    if (nwt <= 320 && pb.fh <= 21 && !getenv("D3D_FORCE_GENERIC")) {
+        c->ne = pb.fh <= 7 ? 7 : pb.fh <= 13 ? 13 : 21;
+        c->threads = ((nwt + 31) / 32) * 32 + 64;
     }
-    c->threads = best_threads;
-    c->ne = best_ne;
+    c->generic_threads = 256;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        c->use_nc = c->ne != 0 && pb.n_chains > sms;
+        if (const char* e = getenv("D3D_ROW_VARIANT")) c->use_nc = c->ne != 0 && atoi(e) == 0;
+    }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
 }
 
@@ -287,9 +294,26 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     } else {
         hk[0] = 1.0;
     }
-    double* d_fsf; double* d_k;
+    // taps that matter: |K[m]| >= 1e-18 max|K| (the dropped ones sum to less than the rounding
+    // error of the kept ones)
+    std::vector<double> tapv; std::vector<int> tapm;
+    {
+        double kmax = 0.0;
+        for (double v : hk) kmax = std::max(kmax, fabs(v));
+        for (int m = 0; m < pb.P; ++m)
+            if (hk[m] != 0.0 && fabs(hk[m]) >= 1e-18 * kmax) { tapv.push_back(hk[m]); tapm.push_back(m); }
+    }
+    pb.ntaps = (int)tapv.size();
+    double* d_fsf; double* d_k; double* d_tv; int* d_tm;
     if ((rc = dalloc(c, &d_fsf, hfsf.size() * sizeof(double)))) return rc;
     if ((rc = dalloc(c, &d_k, hk.size() * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_tv, (tapv.size() + 1) * sizeof(double)))) return rc;
+    if ((rc = dalloc(c, &d_tm, (tapm.size() + 1) * sizeof(int)))) return rc;
+    if (!tapv.empty()) {
+        CK(cudaMemcpy(d_tv, tapv.data(), tapv.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_tm, tapm.data(), tapm.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    pb.ktap_v = d_tv; pb.ktap_m = d_tm;
     CK(cudaMemcpy(d_fsf, hfsf.data(), hfsf.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_k, hk.data(), hk.size() * sizeof(double), cudaMemcpyHostToDevice));
     pb.fsf = d_fsf; pb.kcirc = d_k;
@@ -629,7 +653,7 @@ extern "C" int d3d_delta_logl(d3d_ctx* c, int chain, int y, int x, const double 
 #define LAUNCH_EVAL(T, IV)                                                                        \
     do {                                                                                          \
         cudaFuncSetAttribute(eval_kernel<T, IV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        eval_kernel<T, IV><<<1, c->threads, smem, c->stream>>>(pb, chain, site, ev);              \
+        eval_kernel<T, IV><<<1, c->generic_threads, smem, c->stream>>>(pb, chain, site, ev);              \
     } while (0)
     if (c->dtype == D3D_F64) { if (pb.var_is_cube) LAUNCH_EVAL(double, true); else LAUNCH_EVAL(double, false); }
     else { if (pb.var_is_cube) LAUNCH_EVAL(float, true); else LAUNCH_EVAL(float, false); }
@@ -648,10 +672,23 @@ template <typename T, bool IV, int NE>
 static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep, double min_rate,
                               double* chain_dev, double* lik_dev, long long row_first,
                               long long rows_local) {
-    cudaFuncSetAttribute(sweep_seq_kernel<T, IV, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)c->sweep_smem);
-    sweep_seq_kernel<T, IV, NE><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
-        c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+    if (NE != 0 && c->use_nc) {
+        cudaFuncSetAttribute(sweep_seq_nc_kernel<T, IV>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        sweep_seq_nc_kernel<T, IV><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
+            c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+    } else if (NE == 0) {
+        cudaFuncSetAttribute(sweep_seq_generic_kernel<T, IV>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        sweep_seq_generic_kernel<T, IV><<<c->pb.n_chains, c->generic_threads, c->sweep_smem, c->stream>>>(
+            c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+    } else {
+        const int ne = NE ? NE : 7;    // (never instantiates the row kernel with 0 rows)
+        cudaFuncSetAttribute(sweep_seq_kernel<T, IV, ne>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        sweep_seq_kernel<T, IV, ne><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
+            c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+    }
     c->launches++;
     return cudaGetLastError();
 }
@@ -660,24 +697,33 @@ template <typename T, bool IV, int NE>
 static cudaError_t launch_colour(d3d_ctx* c, long long it, double* chain_dev, double* lik_dev,
                                  long long rows_local, long long row_local) {
     const Problem& pb = c->pb;
-    cudaFuncSetAttribute(sweep_colour_kernel<T, IV, NE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)c->sweep_smem);
+    const int ne = NE ? NE : 7;
+    if (NE == 0)
+        cudaFuncSetAttribute(sweep_colour_generic_kernel<T, IV>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+    else
+        cudaFuncSetAttribute(sweep_colour_kernel<T, IV, ne>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
     const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
     dim3 grid(nly * nlx, pb.n_chains);
     for (int cy = 0; cy < pb.fh; ++cy)
         for (int cx = 0; cx < pb.fw; ++cx) {
             if (cy >= pb.H || cx >= pb.W) continue;
-            sweep_colour_kernel<T, IV, NE><<<grid, c->threads, c->sweep_smem, c->stream>>>(
-                pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
+            if (NE == 0)
+                sweep_colour_generic_kernel<T, IV><<<grid, c->generic_threads, c->sweep_smem, c->stream>>>(
+                    pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
+            else
+                sweep_colour_kernel<T, IV, ne><<<grid, c->threads, c->sweep_smem, c->stream>>>(
+                    pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
             c->launches++;
         }
     return cudaGetLastError();
 }
 
 #define DISPATCH_NE(FN, T, IV, ...)                                         \
-    (c->ne == 4    ? FN<T, IV, 4>(__VA_ARGS__)                              \
-     : c->ne == 8  ? FN<T, IV, 8>(__VA_ARGS__)                              \
-     : c->ne == 16 ? FN<T, IV, 16>(__VA_ARGS__)                             \
+    (c->ne == 7    ? FN<T, IV, 7>(__VA_ARGS__)                              \
+     : c->ne == 13 ? FN<T, IV, 13>(__VA_ARGS__)                             \
+     : c->ne == 21 ? FN<T, IV, 21>(__VA_ARGS__)                             \
                    : FN<T, IV, 0>(__VA_ARGS__))
 #define DISPATCH(FN, ...)                                                                   \
     (c->dtype == D3D_F64                                                                    \

