@@ -53,6 +53,8 @@ struct d3d_ctx {
     double* d_lines = nullptr;          // [n_chains][H][W][Dp] scratch of the forward model
     int threads = 256, ne = 0;          // sweep launch configuration (row-mapped kernels)
     int generic_threads = 256;
+    bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
+    static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
     bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
@@ -177,6 +179,15 @@ static void choose_launch(d3d_ctx* c) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         c->use_nc = c->ne != 0 && pb.n_chains > sms;
         if (const char* e = getenv("D3D_ROW_VARIANT")) c->use_nc = c->ne != 0 && atoi(e) == 0;
+        const int nwt_slide = pb.fw * zl;
+        const int ne_s = c->ne == 0 ? 0 : (c->ne > 13 ? 13 : c->ne);
+        c->slide_threads = ((nwt_slide + 31) / 32) * 32 + 96;
+        // common block + FSF tables per border state + cp.async staging (residual [+ 1/variance])
+        c->slide_smem = c->sweep_smem_base(pb) + (size_t)pb.fh * pb.fh * pb.fw * sizeof(double) +
+                        (size_t)(pb.var_is_cube ? 2 : 1) * pb.fw * ne_s * zl * 16 + 32;
+        c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384 && pb.H >= pb.fh &&
+                       c->slide_smem <= 220 * 1024;
+        if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
 }
@@ -672,7 +683,13 @@ template <typename T, bool IV, int NE>
 static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep, double min_rate,
                               double* chain_dev, double* lik_dev, long long row_first,
                               long long rows_local) {
-    if (NE != 0 && c->use_nc) {
+    if (NE != 0 && c->use_slide) {
+        const int ne = NE ? NE : 7;
+        cudaFuncSetAttribute(sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slide_smem);
+        sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<c->pb.n_chains, c->slide_threads, c->slide_smem, c->stream>>>(
+            c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+    } else if (NE != 0 && c->use_nc) {
         cudaFuncSetAttribute(sweep_seq_nc_kernel<T, IV>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         sweep_seq_nc_kernel<T, IV><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
@@ -843,6 +860,15 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
                                   "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");
     return 0;
 }
+
+#ifdef D3D_PHASE_TIMING
+extern "C" int d3d_debug_phases(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, d3d::g_phase, 32 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(d3d::g_phase, z, sizeof z); }
+    return 0;
+}
+#endif
 
 extern "C" int d3d_get_counters(d3d_ctx* c, int64_t* kernel_launches, int64_t* last_sweep_bytes,
                                 int64_t* last_sweep_site_updates) {

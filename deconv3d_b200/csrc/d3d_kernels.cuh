@@ -85,24 +85,26 @@ struct Smem {
     double* Lu_n;   // [2][Dp]
     double* red;    // [32][8]
     double* bc;     // [8]   decision broadcast: accepted, r, accepted_count, a
-    double* prop;   // [8]   proposal stash of scalar warp B (a, c_old, w_old, a_new, c_new, w_new, log_u, oob)
+    double* prop;   // [2][8] proposal stash
+    double* spec;   // [2][16] pre-evaluated truncated-normal draws (d3d_rng.cuh SP_*) of scalar warp B (a, c_old, w_old, a_new, c_new, w_new, log_u, oob)
 };
 
 __host__ __device__ inline size_t smem_doubles(int fh, int fw, int P, int Dp) {
-    return (size_t)fh * fw + P + (P + 1) / 2 + 6 * (size_t)Dp + 32 * 8 + 8 + 8;
+    return (size_t)fh * fw + P + (P + 1) / 2 + 2 * (size_t)P + 4 * (size_t)Dp + 32 * 8 + 8 + 16 + 32;
 }
 
 __device__ __forceinline__ void carve(Smem& s, double* base, const Problem& pb) {
     s.F = base;
     s.Kv = s.F + pb.fh * pb.fw;
     s.Km = (int*)(s.Kv + pb.P);
-    s.g_o = s.Kv + pb.P + (pb.P + 1) / 2;
-    s.g_n = s.g_o + pb.Dp;
-    s.Lu_o = s.g_n + pb.Dp;
+    s.g_o = s.Kv + pb.P + (pb.P + 1) / 2;      // [P] each (P >= Dp), zero beyond D
+    s.g_n = s.g_o + pb.P;
+    s.Lu_o = s.g_n + pb.P;
     s.Lu_n = s.Lu_o + 2 * pb.Dp;
     s.red = s.Lu_n + 2 * pb.Dp;
     s.bc = s.red + 32 * 8;
     s.prop = s.bc + 8;
+    s.spec = s.prop + 16;
 }
 
 __device__ __forceinline__ void load_constants(Smem& s, const Problem& pb) {
@@ -111,6 +113,7 @@ __device__ __forceinline__ void load_constants(Smem& s, const Problem& pb) {
         s.Kv[i] = pb.ktap_v[i];
         s.Km[i] = pb.ktap_m[i];
     }
+    for (int i = threadIdx.x; i < pb.P; i += blockDim.x) { s.g_o[i] = 0.0; s.g_n[i] = 0.0; }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -122,7 +125,13 @@ __device__ __forceinline__ double warp_sum(double v) {
 // lib/line_models.py:98-109 with a = 1
 __device__ __forceinline__ double unit_gaussian(int z, double c, double w) {
     double d = (double)z - c;
-    return exp(-1.0 * (d * d) / (2.0 * (w * w)));
+    return d_exp(d_div(-1.0 * (d * d), 2.0 * (w * w)));
+}
+// Same with 1/(2 w^2) hoisted out of the channel loop (one divide per line instead of one per
+// channel; the exponent differs from the reference's by at most one ulp).
+__device__ __forceinline__ double unit_gaussian_r(int z, double c, double inv2w2) {
+    double d = (double)z - c;
+    return d_exp(-1.0 * (d * d) * inv2w2);
 }
 
 // lib/convolution.py:89-120 in direct form: out[j] = sum_i g[i] K[(j-i) mod P]
@@ -133,6 +142,18 @@ __device__ __forceinline__ double conv_at(const double* g, const double* K, int 
 }
 
 enum { R_B = 0, R_C, R_PO, R_QOO, R_QON, R_QNN, R_A, R_N };
+
+#ifdef D3D_PHASE_TIMING
+// Debug build only: per-phase clock64() accumulators (window warp 0 / scalar warps, lane 0).
+__device__ unsigned long long g_phase[32];
+#define PH_T0() unsigned long long ph_t = clock64()
+#define PH_ADD(k)                                                                  \
+    do { unsigned long long n_ = clock64(); if (lane == 0 && blockIdx.x == 0)      \
+             atomicAdd(&g_phase[k], n_ - ph_t); ph_t = n_; } while (0)
+#else
+#define PH_T0()
+#define PH_ADD(k)
+#endif
 
 // Spectral convolution on the taps of the circular LSF kernel that matter
 // (|K[m]| >= 1e-18 max|K|, listed by the host): out[j] = sum_m K[m] g[(j-m) mod P].
@@ -156,18 +177,68 @@ __device__ __forceinline__ double conv_taps(const double* g, const double* Kv, c
     return (a0 + a1) + (a2 + a3);
 }
 
+// Two outputs (j0, j1) at once: twice the independent work per tap.
+__device__ __forceinline__ void conv_taps2(const double* g, const double* Kv, const int* Km,
+                                           int ntaps, int j0, int j1, int D, int P, double& o0,
+                                           double& o1) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    int t = 0;
+    for (; t + 1 < ntaps; t += 2) {
+        const int m0 = Km[t], m1 = Km[t + 1];
+        const double k0 = Kv[t], k1 = Kv[t + 1];
+        const int i00 = (j0 - m0) & (P - 1), i01 = (j0 - m1) & (P - 1);
+        const int i10 = (j1 - m0) & (P - 1), i11 = (j1 - m1) & (P - 1);
+        a0 = fma(k0, i00 < D ? g[i00] : 0.0, a0);
+        a1 = fma(k1, i01 < D ? g[i01] : 0.0, a1);
+        b0 = fma(k0, i10 < D ? g[i10] : 0.0, b0);
+        b1 = fma(k1, i11 < D ? g[i11] : 0.0, b1);
+    }
+    if (t < ntaps) {
+        const int m0 = Km[t];
+        const double k0 = Kv[t];
+        const int i00 = (j0 - m0) & (P - 1), i10 = (j1 - m0) & (P - 1);
+        a0 = fma(k0, i00 < D ? g[i00] : 0.0, a0);
+        b0 = fma(k0, i10 < D ? g[i10] : 0.0, b0);
+    }
+    o0 = a0 + a1;
+    o1 = b0 + b1;
+}
+
 // Unit-amplitude line profile Lu = lsf (*) gaussian(c, w) computed by ONE warp:
 // g -> shared (scratch), then the convolution; out[z] for z in [0, Dp).
-__device__ __forceinline__ void warp_line_profile(const Problem& pb, const Smem& sm, double c,
-                                                  double w, double* g, double* out, int lane) {
-    for (int z = lane; z < pb.Dp; z += 32) g[z] = z < pb.D ? unit_gaussian(z, c, w) : 0.0;
+__device__ __noinline__ void warp_line_profile(const Problem& pb, const Smem& sm, double c,
+                                                  double w, double* g, double* out, int lane,
+                                                  int ph_base = -1) {
+#ifdef D3D_PHASE_TIMING
+    unsigned long long ph_t = clock64();
+#define PH_SUB(k) do { unsigned long long n_ = clock64(); if (ph_base >= 0 && lane == 0 && blockIdx.x == 0) atomicAdd(&g_phase[ph_base + k], n_ - ph_t); ph_t = n_; } while (0)
+#else
+#define PH_SUB(k)
+#endif
+    const double inv2w2 = d_div(1.0, 2.0 * (w * w));
+    PH_SUB(0);
+    // two channels per lane and per pass: independent exp() chains overlap
+    for (int z = lane; z < pb.Dp; z += 64) {
+        const int z1 = z + 32;
+        const double g0 = z < pb.D ? unit_gaussian_r(z, c, inv2w2) : 0.0;
+        const double g1 = z1 < pb.D ? unit_gaussian_r(z1, c, inv2w2) : 0.0;
+        g[z] = g0;
+        if (z1 < pb.Dp) g[z1] = g1;
+    }
+    PH_SUB(1);
     __syncwarp();
     if (pb.has_lsf) {
-        for (int z = lane; z < pb.Dp; z += 32)
-            out[z] = z < pb.D ? conv_taps(g, sm.Kv, sm.Km, pb.ntaps, z, pb.D, pb.P) : 0.0;
+        for (int z = lane; z < pb.Dp; z += 64) {
+            const int z1 = z + 32;
+            double o0, o1;
+            conv_taps2(g, sm.Kv, sm.Km, pb.ntaps, z, z1, pb.D, pb.P, o0, o1);
+            out[z] = z < pb.D ? o0 : 0.0;
+            if (z1 < pb.Dp) out[z1] = z1 < pb.D ? o1 : 0.0;
+        }
     } else {                                                        // lib/run.py:675-676
         for (int z = lane; z < pb.Dp; z += 32) out[z] = g[z];
     }
+    PH_SUB(2);
 }
 
 // Proposal of one site (lib/run.py:370-388, 570-579), evaluated redundantly by
@@ -177,7 +248,7 @@ struct Proposal {
     int oob;
 };
 
-__device__ __forceinline__ void make_proposal(const Problem& pb, int chain, int cube, int site,
+__device__ __noinline__ void make_proposal(const Problem& pb, int chain, int cube, int site,
                                               unsigned sweep, const EvalReq& ev, Philox& rng,
                                               Proposal& p) {
     const double* prm = pb.params + ((size_t)chain * pb.H * pb.W + site) * 3;
@@ -190,10 +261,10 @@ __device__ __forceinline__ void make_proposal(const Problem& pb, int chain, int 
         const double q4 = 1.5707963267948966;                       // CIRCLE_4TH, lib/run.py:35
         const double u0 = rng.next(), u1 = rng.next(), u2 = rng.next();
         // numpy's uniform(-q4, q4) is low + (high - low) * u; amplitude jump is 0 (:262)
-        if (pb.jump[0] != 0.0) p.a_new = p.a + pb.jump[0] * tan(-q4 + (q4 - (-q4)) * u0);
-        p.c_new = p.c_old + pb.jump[1] * tan(-q4 + (q4 - (-q4)) * u1);
-        p.w_new = p.w_old + pb.jump[2] * tan(-q4 + (q4 - (-q4)) * u2);
-        p.log_u = log(rng.next());                                  // :435
+        if (pb.jump[0] != 0.0) p.a_new = p.a + pb.jump[0] * d_tan(-q4 + (q4 - (-q4)) * u0);
+        p.c_new = p.c_old + pb.jump[1] * d_tan(-q4 + (q4 - (-q4)) * u1);
+        p.w_new = p.w_old + pb.jump[2] * d_tan(-q4 + (q4 - (-q4)) * u2);
+        p.log_u = d_log(rng.next());                                  // :435
     }
     const double* lo = pb.pmin + cube * 3;
     const double* hi = pb.pmax + cube * 3;
@@ -213,10 +284,10 @@ __device__ __forceinline__ void fetch_proposal(const Smem& sm, Proposal& p) {
 // Accept test + Gibbs draw (lib/run.py:426-451, 456-499) from the reduced sums.
 // Called by all lanes of one warp with identical arguments; lane 0 writes.
 // Returns 1 when the proposal is accepted.
-__device__ __forceinline__ int decide(const Problem& pb, const Smem& sm, int chain, int cube,
+__device__ __noinline__ int decide(const Problem& pb, const Smem& sm, int chain, int cube,
                                       int site, const Proposal& p, const double* tot, Philox& rng,
                                       double* chain_row, double* lik_row, const EvalReq& ev,
-                                      int lane) {
+                                      int lane, const double* spec = nullptr) {
     const double a = p.a, da = p.a_new;
     double delta;
     if (da != a) {
@@ -242,12 +313,25 @@ __device__ __forceinline__ int decide(const Problem& pb, const Smem& sm, int cha
     const double S2 = accepted ? tot[R_QNN] : tot[R_QOO];
     const double S1 = accepted ? (tot[R_PO] - tot[R_B]) + a * tot[R_QON]
                                : tot[R_PO] + a * tot[R_QOO];
-    const double ra = pb.prior_var[cube];                           // :491
-    const double ro = ra / (1.0 + ra * S2);                         // :492
-    const double mu = ro * S1;                                      // :493
     int fail = 0;
-    const double r = rtnorm(pb.pmin[cube * 3], pb.pmax[cube * 3], mu, sqrt(ro), rng, pb.rt,
-                            &fail);                                 // :495-496
+    double r;
+    if (spec) {
+        // ro = ra/(1+ra S2) = 1/q with q = 1/ra + S2; mu = ro S1 = S1/q; sigma = sqrt(ro)
+        // (:491-496).  sqrt(q) and S1/q are independent: the serial chain is one divide long
+        // instead of divide -> sqrt -> divide.
+        const double q = spec[SP_IRA] + S2;
+        const double isg = d_sqrt(q);
+        const double mu = d_div(S1, q);
+        const double sigma = d_div(1.0, isg);
+        r = rtnorm_spec(pb.pmin[cube * 3], pb.pmax[cube * 3], mu, isg, sigma, rng, pb.rt, &fail,
+                        spec);
+    } else {
+        const double ra = pb.prior_var[cube];                       // :491
+        const double ro = d_div(ra, 1.0 + ra * S2);                 // :492
+        const double mu = ro * S1;                                  // :493
+        r = rtnorm(pb.pmin[cube * 3], pb.pmax[cube * 3], mu, d_sqrt(ro), rng, pb.rt,
+                   &fail);                                          // :495-496
+    }
     if (lane == 0) {
         if (fail) atomicExch(pb.status, 1);
         double* prm = pb.params + ((size_t)chain * pb.H * pb.W + site) * 3;
@@ -329,8 +413,10 @@ struct RowSite {
         const double* frow = sm.F + oy * pb.fw + ox + dx;
         const size_t rstride = (size_t)W * Dp;
 
+        PH_T0();
         if (winwarp) {
             bar_sync_named(1, nww * 32);          // previous update visible to every window warp
+            if (warp == 0) PH_ADD(0);             // [0] named barrier
             if (active) {
                 const size_t base = ((size_t)y0 * W + x0 + dx) * Dp + zp * VEC;
                 erow = (T*)pb.err + (size_t)chain * H * W * Dp + base;
@@ -447,14 +533,20 @@ struct RowSite {
         } else if (warpA) {
             const double* prm = pb.params + ((size_t)chain * H * W + site) * 3;
             warp_line_profile(pb, sm, prm[1], prm[2], sm.g_o, Lu_o, lane);
+            PH_ADD(8);                            // [8] warp A prep
         } else if (warpB) {
             Philox rng;
             Proposal prop;
             make_proposal(pb, chain, cube, site, sweep, ev, rng, prop);
             if (lane == 0) stash_proposal(sm, prop);
+            PH_ADD(9);                            // [9] warp B proposal
             warp_line_profile(pb, sm, prop.c_new, prop.w_new, sm.g_n, Lu_n, lane);
+            PH_ADD(10);                           // [10] warp B new profile
         }
+        if (winwarp && warp == 0) PH_ADD(1);      // [1] window loads + sums
         __syncthreads();                                                        // B1
+        if (winwarp && warp == 0) PH_ADD(2);      // [2] wait B1
+        if (warpB) PH_ADD(11);                    // [11] warp B wait B1
 
         if (winwarp) {
             double lo_v[VEC], ln_v[VEC];
@@ -483,7 +575,10 @@ struct RowSite {
                 if (lane == 0) sm.red[warp * 8 + j] = s;
             }
         }
+        if (winwarp && warp == 0) PH_ADD(3);      // [3] partials
         __syncthreads();                                                        // B2
+        if (winwarp && warp == 0) PH_ADD(4);      // [4] wait B2
+        if (warpB) PH_ADD(12);                    // [12] warp B wait B2
 
         if (warpB) {
             double tot[R_N];
@@ -497,10 +592,13 @@ struct RowSite {
             Philox rng;                      // draws 0..3 went into the proposal (make_proposal)
             rng.init(pb.seed, pb.first_chain + (unsigned)chain, sweep, (unsigned)site);
             rng.k = 4;
+            PH_ADD(13);                           // [13] totals
             accepted = decide(pb, sm, chain, cube, site, prop, tot, rng, chain_row, lik_row, ev,
                               lane);
+            PH_ADD(14);                           // [14] decide
         }
         __syncthreads();                                                        // B3
+        if (winwarp && warp == 0) PH_ADD(5);      // [5] wait B3
         if (ev.enabled) return 0;
 
         if (active) {
@@ -557,6 +655,7 @@ struct RowSite {
                 }
             }
         }
+        if (winwarp && warp == 0) PH_ADD(6);      // [6] update
         return accepted;
     }
 };
@@ -741,7 +840,7 @@ __device__ __forceinline__ int site_update_generic(const Problem& pb, const Smem
 // ---------------------------------------------------------------------------
 template <typename T, bool IVCUBE, int NE>
 __global__ void __launch_bounds__(384, 1)
-sweep_seq_kernel(Problem pb, long long it0, long long it1, int keep, double min_rate,
+sweep_seq_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep, double min_rate,
                  double* chain_out, double* lik_out, long long row_first, long long rows_local) {
     D3D_SEQ_PROLOGUE()
     RowSite<T, IVCUBE, NE, false> rs;
@@ -779,7 +878,7 @@ sweep_seq_kernel(Problem pb, long long it0, long long it1, int keep, double min_
 // chains share the GPU so that the serial phases of one chain hide behind another's.
 template <typename T, bool IVCUBE>
 __global__ void __launch_bounds__(384, 2)
-sweep_seq_nc_kernel(Problem pb, long long it0, long long it1, int keep, double min_rate,
+sweep_seq_nc_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep, double min_rate,
                     double* chain_out, double* lik_out, long long row_first, long long rows_local) {
     D3D_SEQ_PROLOGUE()
     RowSite<T, IVCUBE, 0, false> rs;
@@ -814,7 +913,7 @@ sweep_seq_nc_kernel(Problem pb, long long it0, long long it1, int keep, double m
 }
 
 template <typename T, bool IVCUBE>
-__global__ void sweep_seq_generic_kernel(Problem pb, long long it0, long long it1, int keep,
+__global__ void sweep_seq_generic_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep,
                                          double min_rate, double* chain_out, double* lik_out,
                                          long long row_first, long long rows_local) {
     D3D_SEQ_PROLOGUE()
@@ -853,7 +952,7 @@ __global__ void sweep_seq_generic_kernel(Problem pb, long long it0, long long it
 // (site, chain) updates them concurrently.  sweep_begin_kernel evaluates the
 // loop condition of lib/run.py:344-359 once per iteration.
 // ---------------------------------------------------------------------------
-__global__ void sweep_begin_kernel(Problem pb, long long it, double min_rate) {
+__global__ void sweep_begin_kernel(const __grid_constant__ Problem pb, long long it, double min_rate) {
     int chain = blockIdx.x * blockDim.x + threadIdx.x;
     if (chain >= pb.n_chains || !pb.active[chain]) return;
     double rate = pb.rate[chain];
@@ -886,7 +985,7 @@ __global__ void sweep_begin_kernel(Problem pb, long long it, double min_rate) {
 
 template <typename T, bool IVCUBE, int NE>
 __global__ void __launch_bounds__(384, 1)
-sweep_colour_kernel(Problem pb, long long it, int cy, int cx, int nlx, double* crow_base,
+sweep_colour_kernel(const __grid_constant__ Problem pb, long long it, int cy, int cx, int nlx, double* crow_base,
                     double* lrow_base, long long rows_local, long long row_local) {
     D3D_COLOUR_PROLOGUE()
     RowSite<T, IVCUBE, NE, false> rs;
@@ -896,7 +995,7 @@ sweep_colour_kernel(Problem pb, long long it, int cy, int cx, int nlx, double* c
 }
 
 template <typename T, bool IVCUBE>
-__global__ void sweep_colour_generic_kernel(Problem pb, long long it, int cy, int cx, int nlx,
+__global__ void sweep_colour_generic_kernel(const __grid_constant__ Problem pb, long long it, int cy, int cx, int nlx,
                                             double* crow_base, double* lrow_base,
                                             long long rows_local, long long row_local) {
     D3D_COLOUR_PROLOGUE()
@@ -906,7 +1005,7 @@ __global__ void sweep_colour_generic_kernel(Problem pb, long long it, int cy, in
 }
 
 template <typename T, bool IVCUBE>
-__global__ void eval_kernel(Problem pb, int chain, int site, EvalReq ev) {
+__global__ void eval_kernel(const __grid_constant__ Problem pb, int chain, int site, EvalReq ev) {
     extern __shared__ double smem_raw[];
     Smem sm;
     carve(sm, smem_raw, pb);
@@ -921,7 +1020,7 @@ __global__ void eval_kernel(Problem pb, int chain, int site, EvalReq ev) {
 // ---------------------------------------------------------------------------
 // Pass 1 (spectral): lines[chain][y][x][Dp] = mask * a * (lsf (*) gaussian(c,w)); one warp
 // per spaxel, the Gaussian is exchanged through shared memory.
-__global__ void lines_kernel(Problem pb, const double* params, double* lines, int convolve) {
+__global__ void lines_kernel(const __grid_constant__ Problem pb, const double* params, double* lines, int convolve) {
     extern __shared__ double smem_raw[];
     double* K = smem_raw;                         // [P]
     double* g = K + pb.P;                         // [warps][Dp]
@@ -962,7 +1061,7 @@ __global__ void lines_kernel(Problem pb, const double* params, double* lines, in
 // every output accumulates fh*fw taps from it.  Fused epilogue: residual =
 // data - sim, optional sim output in the reference layout, optional chi^2.
 template <typename T>
-__global__ void stencil_zchunk_kernel(Problem pb, const double* lines, double* sim_out,
+__global__ void stencil_zchunk_kernel(const __grid_constant__ Problem pb, const double* lines, double* sim_out,
                                       int write_err, double* chi2_out, int TY, int TX, int ZC) {
     extern __shared__ double smem_raw[];
     const int fh = pb.fh, fw = pb.fw, Dp = pb.Dp, D = pb.D, H = pb.H, W = pb.W;
@@ -1022,7 +1121,7 @@ __global__ void stencil_zchunk_kernel(Problem pb, const double* lines, double* s
 }
 
 // un-convolved lines in the reference layout (lib/run.py:597-621)
-__global__ void clean_kernel(Problem pb, const double* params, double* out) {
+__global__ void clean_kernel(const __grid_constant__ Problem pb, const double* params, double* out) {
     const size_t HW = (size_t)pb.H * pb.W;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)pb.n_chains * pb.D * HW;
@@ -1107,7 +1206,7 @@ __global__ void egest_kernel(const T* src, double* dst, int n, int D, int Dp, in
 }
 
 // Initial parameters uniform in the boundaries (lib/run.py:308-314), sweep 0.
-__global__ void init_params_kernel(Problem pb) {
+__global__ void init_params_kernel(const __grid_constant__ Problem pb) {
     const size_t HW = (size_t)pb.H * pb.W;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)pb.n_chains * HW) return;
@@ -1156,3 +1255,5 @@ __global__ void conv1d_kernel(const double* lines, const double* kcirc, double* 
 }
 
 }  // namespace d3d
+
+#include "d3d_slide.cuh"

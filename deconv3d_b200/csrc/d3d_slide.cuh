@@ -1,0 +1,531 @@
+// d3d_slide.cuh -- SEQ_EXACT sweep with a register-resident sliding window.
+//
+// In the reference's row-major sweep (lib/run.py:553-566) consecutive proposals
+// move the FSF window by one spaxel: fw-1 of its fw columns are shared.  This
+// kernel keeps the whole window of the chain -- residual AND 1/variance -- in
+// registers across sites:
+//
+//   * (fw+1) column groups of ZL = Dp/VEC threads; group r owns the window
+//     column X with X = r (mod fw+1) and keeps its fh rows in registers
+//     (one 16-byte vector per row);
+//   * per site only the group whose column left the window writes it back and
+//     loads the column that will ENTER the window at the next site (the window
+//     is fw wide, fw+1 columns are resident), so the load latency overlaps a
+//     whole site update and HBM/L2 traffic drops from 3*fh*fw to ~3*fh vectors
+//     per site (all columns are reloaded when the row changes);
+//   * the sums h[z], G[z] (d3d_kernels.cuh header) and the residual update are
+//     pure register arithmetic.
+//
+// Warp roles (named barriers, PTX bar.sync / bar.arrive):
+//   W  window warps                       sums, partial reduction, update
+//   A  old line profile  Lu(c_old,w_old)  } run up to two sites ahead of the
+//   P  proposal (Philox, Cauchy jump) +   } decisions, double-buffered in smem
+//      new line profile  Lu(c_new,w_new)  }
+//   B  accept test + truncated-normal Gibbs draw
+// Barrier ids: 2,3 READY[parity] (A,P arrive; W,B wait)  4,5 FREE[parity]
+// (W,B arrive two sites later; A,P wait)  6 partials ready (W,B)  7 decision
+// broadcast (W,B).  Look-ahead never crosses a sweep boundary, where the
+// acceptance-rate test of lib/run.py:344-359 needs the finished sweep.
+#pragma once
+
+namespace d3d {
+
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 8 per-lane partial sums -> 8 warp totals with 7 double shuffles (instead of 8 x 5):
+// each round halves the number of slots a lane is responsible for.  On return the
+// lanes with (lane & 3) == 0 hold the total of slot ((lane >> 2) & 7) in `out`.
+__device__ __forceinline__ double warp_sum8(const double* v, int lane) {
+    double w4[4], w2[2], w1;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = b4 ? v[i] : v[i + 4];
+        const double keep = b4 ? v[i + 4] : v[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = b3 ? w4[i] : w4[i + 2];
+        const double keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const double send = b2 ? w2[0] : w2[1];
+        const double keep = b2 ? w2[1] : w2[0];
+        w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+    w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+    return w1;      // slot index = b4*4 + b3*2 + b2
+}
+__device__ __forceinline__ int warp_sum8_slot(int lane) {
+    return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+}
+
+template <typename T, bool IVCUBE, int NE>
+__global__ void __launch_bounds__(384, 1)
+sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep, double min_rate,
+                       double* chain_out, double* lik_out, long long row_first,
+                       long long rows_local) {
+    typedef typename Vec<T>::V V;
+    const int VEC = Vec<T>::N;
+    extern __shared__ double smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    const int chain = blockIdx.x;
+    if (chain >= pb.n_chains) return;
+    const int cube = chain / pb.chains_per_cube;
+    if (!pb.active[chain]) return;
+    load_constants(sm, pb);
+    if (threadIdx.x == 0) sm.bc[2] = (double)pb.accepted[chain];
+    __syncthreads();
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Dp = pb.Dp, W = pb.W, H = pb.H, fw = pb.fw, fh = pb.fh;
+    const int ZL = Dp / VEC;
+    const int nwt = fw * ZL;                       // fw column groups of ZL threads
+    const int nww = (nwt + 31) >> 5;
+    const bool roleW = warp < nww, roleA = warp == nww, roleP = warp == nww + 1,
+               roleB = warp == nww + 2;
+    const int cntAll = (nww + 3) * 32, cntWB = (nww + 1) * 32;
+    const int grp = tid / ZL, zp = tid - grp * ZL;
+    const bool wt = tid < nwt;
+
+    const int ns = pb.n_sites[cube];
+    const int* sites = pb.sites + (size_t)cube * pb.max_sites;
+    const size_t HW = (size_t)H * W;
+    const size_t rstride = (size_t)W * Dp;
+    T* const err = (T*)pb.err + (size_t)chain * HW * Dp;
+    const T* const ivc = IVCUBE ? (const T*)pb.iv + (size_t)cube * HW * Dp : nullptr;
+    const double ivs = IVCUBE ? 0.0 : pb.iv_scalar[cube];
+    const double ira = 1.0 / pb.prior_var[cube];
+
+    // Column groups: fw groups of ZL threads, group r owns the window column X = r (mod fw)
+    // and keeps its fh rows (residual, and 1/variance) in registers.  The column that enters
+    // the window at the NEXT site is prefetched with cp.async into a private shared-memory
+    // staging slot, so its latency never blocks the register scoreboard of the warp.
+    V ecache[NE];
+    V ivcache[IVCUBE ? NE : 1];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { ecache[i] = V(); if (IVCUBE) ivcache[i] = V(); }
+    const int NOCOL = -(1 << 30);
+    int heldX = NOCOL, heldY = NOCOL, pendX = NOCOL, pendY = NOCOL;
+    // shared memory beyond the common block: FSF tables per border state, staging slots
+    double* const Ftab = smem_raw + smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp);
+    V* const stage_e = (V*)(((size_t)(Ftab + (size_t)fh * fh * fw) + 15) & ~(size_t)15) +
+                       ((size_t)grp * NE) * ZL + zp;
+    V* const stage_v = stage_e + (size_t)fw * NE * ZL;
+    // Ftab[s][i][dx] = F[i][dx] with the rows that fall outside the cube zeroed:
+    // s = 0 interior, s = t (1..fhh) t rows clipped at the top, s = fhh + b b rows at the bottom
+    for (int q = tid; q < fh * fh * fw; q += blockDim.x) {
+        const int st = q / (fh * fw), rem = q - st * fh * fw, i = rem / fw;
+        const int top = st <= pb.fhh ? st : 0, bot = st > pb.fhh ? st - pb.fhh : 0;
+        Ftab[q] = (i >= top && i < fh - bot) ? sm.F[rem] : 0.0;
+    }
+    __syncthreads();
+
+    double rate = pb.rate[chain];
+    long long accepted = pb.accepted[chain];       // owned by warp B
+    long long it = it0;
+    int alive = 1;
+
+    for (; it < it1; ++it) {
+        if (!(rate > min_rate || rate == 0.0)) { alive = 0; break; }   // lib/run.py:344-350
+        const double max_acc = (double)ns * (double)it;                // :356-359
+        if (max_acc > 0.0) rate = sm.bc[2] / max_acc;
+        const bool save = (it % keep) == 0;                            // :353
+        double* crow = nullptr; double* lrow = nullptr;
+        if (save) {
+            long long r = it / keep - row_first;
+            if (chain_out) crow = chain_out + ((size_t)chain * rows_local + r) * HW * 3;
+            if (lik_out) lrow = lik_out + ((size_t)chain * rows_local + r) * HW;
+        }
+
+        for (int j = 0; j < ns; ++j) {
+            const int par = j & 1;
+            const int site = sites[j];
+            const int y = site / W, x = site - y * W;
+            double* Lu_o = sm.Lu_o + par * Dp;
+            double* Lu_n = sm.Lu_n + par * Dp;
+            double* prop_s = sm.prop + par * 8;
+            double* spec_s = sm.spec + par * 16;
+
+            PH_T0();
+            if (roleW) {
+                // ---- make the resident column of this thread current for (y, x) ---------
+                const int top = max(0, pb.fhh - y), bot = max(0, y + pb.fhh - (H - 1));
+                const double* ftab = Ftab + (top ? top : (bot ? pb.fhh + bot : 0)) * fh * fw;
+                const int xl = x - pb.fhw;
+                int m = (grp - xl) % fw;
+                if (m < 0) m += fw;
+                const int Xn = xl + m;                           // the window column = grp (mod fw)
+                if (wt && (Xn != heldX || y != heldY)) {
+                    if (heldX >= 0 && heldX < W) {               // old column back to memory
+                        const int ytop = heldY - pb.fhh;
+                        const int lo = max(0, -ytop), n = min(fh, H - ytop) - lo;
+                        char* p = (char*)(err + ((long long)ytop * W + heldX) * Dp + zp * VEC);
+#pragma unroll
+                        for (int i = 0; i < NE; ++i)
+                            if ((unsigned)(i - lo) < (unsigned)n)
+                                *(V*)(p + (size_t)i * rstride * sizeof(T)) = ecache[i];
+                    }
+                    if (Xn >= 0 && Xn < W) {
+                        const int ytop = y - pb.fhh;
+                        const int lo = top, n = fh - bot - top;
+                        if (pendX == Xn && pendY == y) {         // prefetched at the previous site
+                            asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+                            for (int i = 0; i < NE; ++i)
+                                if ((unsigned)(i - lo) < (unsigned)n) {
+                                    ecache[i] = stage_e[i * ZL];
+                                    if (IVCUBE) ivcache[i] = stage_v[i * ZL];
+                                }
+                        } else {                                 // first site of a launch / jumps
+                            const long long off = ((long long)ytop * W + Xn) * Dp + zp * VEC;
+                            const char* p = (const char*)(err + off);
+                            const char* q = IVCUBE ? (const char*)(ivc + off) : nullptr;
+#pragma unroll
+                            for (int i = 0; i < NE; ++i)
+                                if ((unsigned)(i - lo) < (unsigned)n) {
+                                    ecache[i] = *(const V*)(p + (size_t)i * rstride * sizeof(T));
+                                    if (IVCUBE)
+                                        ivcache[i] = *(const V*)(q + (size_t)i * rstride * sizeof(T));
+                                }
+                        }
+                    }
+                    heldX = Xn; heldY = y;
+                }
+                // ---- prefetch the column this thread will need at the next site ----------
+                if (wt && j + 1 < ns) {
+                    const int site2 = sites[j + 1];
+                    const int y2 = site2 / W, x2 = site2 - y2 * W;
+                    const int xl2 = x2 - pb.fhw;
+                    int m2 = (grp - xl2) % fw;
+                    if (m2 < 0) m2 += fw;
+                    const int X2 = xl2 + m2;
+                    // (same column on another row is still dirty in registers: no prefetch)
+                    if (X2 != heldX && X2 >= 0 && X2 < W) {
+                        const int ytop = y2 - pb.fhh;
+                        const int lo = max(0, -ytop), n = min(fh, H - ytop) - lo;
+                        const long long off = ((long long)ytop * W + X2) * Dp + zp * VEC;
+                        const char* p = (const char*)(err + off);
+                        const char* q = IVCUBE ? (const char*)(ivc + off) : nullptr;
+                        const unsigned se = (unsigned)__cvta_generic_to_shared(stage_e);
+                        const unsigned sv = (unsigned)__cvta_generic_to_shared(stage_v);
+#pragma unroll
+                        for (int i = 0; i < NE; ++i)
+                            if ((unsigned)(i - lo) < (unsigned)n) {
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                                                 se + (unsigned)(i * ZL * 16)),
+                                             "l"(p + (size_t)i * rstride * sizeof(T))
+                                             : "memory");
+                                if (IVCUBE)
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                                                     sv + (unsigned)(i * ZL * 16)),
+                                                 "l"(q + (size_t)i * rstride * sizeof(T))
+                                                 : "memory");
+                            }
+                        pendX = X2; pendY = y2;
+                    }
+                }
+                // ---- window sums (registers only; clipped rows have F = 0 in ftab) --------
+                const int dx = heldX - xl;
+                const bool active = wt && heldX >= 0 && heldX < W;   // dx in [0, fw) by construction
+                double part[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) part[k] = 0.0;
+                double h[VEC], g[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
+                const double* fcol = ftab + (active ? dx : 0);
+                if (active) {
+                    double f2 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) {
+                        if (i < fh) {
+                            const double f = fcol[i * fw];
+                            double e[VEC];
+                            unpack(ecache[i], e);
+                            if (IVCUBE) {
+                                double w_[VEC];
+                                unpack(ivcache[i], w_);
+                                const double ff = f * f;
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) {
+                                    h[v] = fma(f * w_[v], e[v], h[v]);
+                                    g[v] = fma(ff, w_[v], g[v]);
+                                }
+                            } else {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) h[v] = fma(f, e[v], h[v]);
+                                f2 = fma(f, f, f2);
+                            }
+                        }
+                    }
+                    if (!IVCUBE) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { h[v] *= ivs; g[v] = ivs * f2; }
+                    }
+                }
+                if (warp == 0) PH_ADD(0);                        // [0] W columns + sums
+                bar_sync_named(2 + par, cntAll);                 // READY: profiles of site j
+                if (warp == 0) PH_ADD(1);                        // [1] W wait READY
+                double lo_v[VEC], ln_v[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    lo_v[v] = Lu_o[zp * VEC + v];
+                    ln_v[v] = Lu_n[zp * VEC + v];
+                    if (active) {
+                        const double dl = lo_v[v] - ln_v[v];
+                        part[R_B] = fma(dl, h[v], part[R_B]);
+                        part[R_PO] = fma(lo_v[v], h[v], part[R_PO]);
+                        part[R_C] = fma(dl * dl, g[v], part[R_C]);
+                        part[R_QOO] = fma(lo_v[v] * lo_v[v], g[v], part[R_QOO]);
+                        part[R_QON] = fma(lo_v[v] * ln_v[v], g[v], part[R_QON]);
+                        part[R_QNN] = fma(ln_v[v] * ln_v[v], g[v], part[R_QNN]);
+                    }
+                }
+                {
+                    const double tot = warp_sum8(part, lane);
+                    if ((lane & 3) == 0) sm.red[warp * 8 + warp_sum8_slot(lane)] = tot;
+                }
+                if (warp == 0) PH_ADD(2);                        // [2] W partials
+                bar_sync_named(6, cntWB);                        // partials visible to B
+                if (warp == 0) PH_ADD(3);                        // [3] W wait bar6
+                bar_sync_named(7, cntWB);                        // decision broadcast
+                if (warp == 0) PH_ADD(4);                        // [4] W wait decision
+                if (active) {
+                    const int acc = sm.bc[0] != 0.0;
+                    const double r = sm.bc[1], a = sm.bc[3];
+                    double coef[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v)
+                        coef[v] = a * lo_v[v] - r * (acc ? ln_v[v] : lo_v[v]);
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) {
+                        if (i < fh) {                            // F = 0 on clipped rows: no-op there
+                            const double f = fcol[i * fw];
+                            double e[VEC];
+                            unpack(ecache[i], e);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                            pack(ecache[i], e);
+                        }
+                    }
+                }
+                if (warp == 0) PH_ADD(5);                        // [5] W update
+                if (j + 2 < ns) bar_arrive_named(4 + par, cntAll);   // FREE: buffers of site j
+            } else if (roleB) {
+                bar_sync_named(2 + par, cntAll);
+                bar_sync_named(6, cntWB);
+                PH_ADD(6);                                       // [6] B waits
+                // totals: lane s < 8 owns slot s and adds the nww warp partials
+                double t = 0.0;
+                if (lane < 8)
+                    for (int wv = 0; wv < nww; ++wv) t += sm.red[wv * 8 + lane];
+                double tot[R_N];
+#pragma unroll
+                for (int k = 0; k < R_N; ++k) tot[k] = __shfl_sync(0xffffffffu, t, k);
+                const double a = prop_s[0], c_old = prop_s[1], w_old = prop_s[2];
+                const double a_new = prop_s[3], c_new = prop_s[4], w_new = prop_s[5];
+                const bool oob = prop_s[7] != 0.0;
+                const double log_u = spec_s[SP_LOGU];
+                PH_ADD(7);                                       // [7] B totals
+                // accept test (lib/run.py:426-451)
+                double delta;
+                if (a_new != a) {
+                    const double Pn = tot[R_PO] - tot[R_B];
+                    const double Bq = a * tot[R_PO] - a_new * Pn;
+                    const double Cq = a * a * tot[R_QOO] - 2.0 * a * a_new * tot[R_QON] +
+                                      a_new * a_new * tot[R_QNN];
+                    delta = -Bq - 0.5 * Cq;
+                } else {
+                    delta = -(a * tot[R_B]) - 0.5 * (a * a) * tot[R_C];
+                }
+                const int acc = (log_u < delta) && !oob;                        // :438
+                const double c_end = acc ? c_new : c_old, w_end = acc ? w_new : w_old;
+                const double S2 = acc ? tot[R_QNN] : tot[R_QOO];
+                const double S1 = acc ? (tot[R_PO] - tot[R_B]) + a * tot[R_QON]
+                                      : tot[R_PO] + a * tot[R_QOO];
+                // Gibbs draw (lib/run.py:491-496): ro = ra/(1+ra S2) = 1/q, q = 1/ra + S2;
+                // sigma = sqrt(ro) = rsqrt(q): ONE serial slow operation instead of
+                // divide -> sqrt -> divide; mu = ro S1.
+                const double q = ira + S2;
+                const double sg = rsqrt(q);
+                const double isg = q * sg;
+                const double mu = S1 * (sg * sg);
+                const double lo = pb.pmin[cube * 3], hi = pb.pmax[cube * 3];
+                const double as = (lo - mu) * isg, bs = (hi - mu) * isg;   // lib/rtnorm.py:74-76
+                double rs;
+                int fail = 0;
+                bool done = false;
+                const bool plain = (as < bs) && !(fabs(as) > fabs(bs));   // no mirror (:108)
+                if (plain && as < -2.00443204036) {                        // :127-131
+                    // Gaussian proposal; the first two normals were evaluated ahead
+                    const double n1 = spec_s[SP_N1], n2 = spec_s[SP_N2];
+                    if (n1 >= as && n1 <= bs) { rs = n1; done = true; }
+                    else if (n2 >= as && n2 <= bs) { rs = n2; done = true; }
+                } else if (plain && as > 3.48672170399 && -as * (bs - as) < -40.0) {   // :112-124
+                    // right tail with exp(-a(b-a)) below 2^-54: expab == -1 exactly, so the
+                    // first z = log(1 - u) and e = -log(u') were evaluated ahead
+                    const double z = spec_s[SP_Z1];
+                    if (2.0 * as * as * spec_s[SP_E1] > z * z) { rs = as - z / as; done = true; }
+                }
+                if (!done) {                                     // every other branch / retry
+                    Philox rng;
+                    rng.init(pb.seed, pb.first_chain + (unsigned)chain, (unsigned)it,
+                             (unsigned)site);
+                    rng.k = 4;
+                    rng.stash = spec_s;
+                    rs = rtstdnorm(as, bs, rng, pb.rt, &fail, nullptr);
+                }
+                const double r = rs * sg + mu;                                  // :82-83
+                if (lane == 0) {
+                    if (fail) atomicExch(pb.status, 1);
+                    double* prm = pb.params + ((size_t)chain * HW + site) * 3;
+                    prm[0] = r; prm[1] = c_end; prm[2] = w_end;                 // :448,:499,:516
+                    if (crow) { double* cr = crow + (size_t)site * 3; cr[0] = r; cr[1] = c_end; cr[2] = w_end; }
+                    if (lrow) lrow[site] = delta;                               // :430-432
+                    sm.bc[0] = acc ? 1.0 : 0.0;
+                    sm.bc[1] = r;
+                    sm.bc[3] = a;
+                    accepted += acc;
+                    if (j == ns - 1) sm.bc[2] = (double)accepted;
+                }
+                PH_ADD(8);                                       // [8] B decide
+                bar_sync_named(7, cntWB);
+                if (j + 2 < ns) bar_arrive_named(4 + par, cntAll);
+            } else if (roleA || roleP) {
+                if (j >= 2) bar_sync_named(4 + par, cntAll);     // buffers of this parity free
+                PH_ADD(9);                                       // [9] A/P wait FREE
+                const double* prm = pb.params + ((size_t)chain * HW + site) * 3;
+                const double a = prm[0], c_old = prm[1], w_old = prm[2];
+                // Philox blocks 0..3 in lanes 0..3: draws (2b, 2b+1) of this site
+                unsigned o[4];
+                philox_block_inl((unsigned)pb.seed, (unsigned)(pb.seed >> 32), (unsigned)(lane & 3),
+                                 (unsigned)site, (unsigned)it, pb.first_chain + (unsigned)chain, o);
+                const double ua = Philox::u53(o[0], o[1]), ub = Philox::u53(o[2], o[3]);
+                double c_prof, w_prof;
+                double* g_buf; double* Lu_out;
+                if (roleP) {
+                    // ---- proposal: Cauchy jump (lib/run.py:570-579), one tan() for all lanes
+                    const double u0 = __shfl_sync(0xffffffffu, ua, 0);
+                    const double u1 = __shfl_sync(0xffffffffu, ub, 0);
+                    const double u2 = __shfl_sync(0xffffffffu, ua, 1);
+                    const double q4 = 1.5707963267948966;
+                    const double targ = lane == 0 ? u1 : (lane == 1 ? u2 : u0);
+                    const double tv = tan(-q4 + (q4 - (-q4)) * targ);
+                    const double t1 = __shfl_sync(0xffffffffu, tv, 0);
+                    const double t2 = __shfl_sync(0xffffffffu, tv, 1);
+                    const double t0 = __shfl_sync(0xffffffffu, tv, 2);
+                    const double a_new = pb.jump[0] != 0.0 ? a + pb.jump[0] * t0 : a;
+                    const double c_new = c_old + pb.jump[1] * t1;
+                    const double w_new = w_old + pb.jump[2] * t2;
+                    const double* lo = pb.pmin + cube * 3;
+                    const double* hi = pb.pmax + cube * 3;
+                    const int oob = (a_new < lo[0]) | (c_new < lo[1]) | (w_new < lo[2]) |
+                                    (a_new > hi[0]) | (c_new > hi[1]) | (w_new > hi[2]);
+                    if (lane == 0) {
+                        prop_s[0] = a; prop_s[1] = c_old; prop_s[2] = w_old;
+                        prop_s[3] = a_new; prop_s[4] = c_new; prop_s[5] = w_new;
+                        prop_s[7] = (double)oob;
+                    }
+                    c_prof = c_new; w_prof = w_new; g_buf = sm.g_n; Lu_out = Lu_n;
+                    PH_ADD(12);                                  // [12] P proposal
+                } else {
+                    // ---- accept uniform + first truncated-normal draws, lane-parallel:
+                    // five logs in one log(), two sqrt in one sqrt(), two cos in one cos()
+                    const double u3 = __shfl_sync(0xffffffffu, ub, 1);
+                    const double u4 = __shfl_sync(0xffffffffu, ua, 2);
+                    const double u5 = __shfl_sync(0xffffffffu, ub, 2);
+                    const double u6 = __shfl_sync(0xffffffffu, ua, 3);
+                    const double u7 = __shfl_sync(0xffffffffu, ub, 3);
+                    const double r4 = 1e-15 + (1.0 - 1e-15) * u4, r5 = 1e-15 + (1.0 - 1e-15) * u5;
+                    const double larg = lane == 0 ? u3 : lane == 1 ? r5 : lane == 2 ? 1.0 + r4 * -1.0
+                                      : lane == 3 ? 1.0 - u4 : 1.0 - u6;
+                    const double lv = log(larg);
+                    const double l4 = __shfl_sync(0xffffffffu, lv, 3);
+                    const double l6 = __shfl_sync(0xffffffffu, lv, 4);
+                    const double sv = sqrt(-2.0 * (lane == 0 ? l4 : l6));
+                    const double cv = cos(6.283185307179586 * (lane == 0 ? u5 : u7));
+                    const double nv = sv * cv;
+                    const double n2 = __shfl_sync(0xffffffffu, nv, 1);
+                    const double e1 = -__shfl_sync(0xffffffffu, lv, 1);
+                    const double z1 = __shfl_sync(0xffffffffu, lv, 2);
+                    if (lane == 0) {
+                        spec_s[SP_U4] = u4; spec_s[SP_U5] = u5; spec_s[SP_U6] = u6; spec_s[SP_U7] = u7;
+                        spec_s[SP_E1] = e1; spec_s[SP_Z1] = z1; spec_s[SP_N1] = nv; spec_s[SP_N2] = n2;
+                        spec_s[SP_LOGU] = lv;
+                    }
+                    c_prof = c_old; w_prof = w_old; g_buf = sm.g_o; Lu_out = Lu_o;
+                    PH_ADD(10);                                  // [10] A draws
+                }
+                // ---- unit line profile Lu = lsf (*) exp(-(z-c)^2 / (2 w^2)) -------------
+                {
+                    const double inv2w2 = 1.0 / (2.0 * (w_prof * w_prof));
+                    const int D = pb.D, P = pb.P;
+                    for (int z = lane; z < Dp; z += 64) {
+                        const int z1 = z + 32;
+                        const double d0 = (double)z - c_prof, d1 = (double)z1 - c_prof;
+                        const double g0 = exp(-1.0 * (d0 * d0) * inv2w2);
+                        const double g1 = exp(-1.0 * (d1 * d1) * inv2w2);
+                        if (z < D) g_buf[z] = g0;
+                        if (z1 < D) g_buf[z1] = g1;
+                    }
+                    __syncwarp();
+                    if (pb.has_lsf) {
+                        const int nt = pb.ntaps;
+                        for (int z = lane; z < Dp; z += 64) {
+                            const int z1 = z + 32;
+                            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+                            int tq = 0;
+                            for (; tq + 1 < nt; tq += 2) {
+                                const int m0 = sm.Km[tq], m1 = sm.Km[tq + 1];
+                                const double k0 = sm.Kv[tq], k1 = sm.Kv[tq + 1];
+                                a0 = fma(k0, g_buf[(z - m0) & (P - 1)], a0);
+                                a1 = fma(k1, g_buf[(z - m1) & (P - 1)], a1);
+                                b0 = fma(k0, g_buf[(z1 - m0) & (P - 1)], b0);
+                                b1 = fma(k1, g_buf[(z1 - m1) & (P - 1)], b1);
+                            }
+                            if (tq < nt) {
+                                const int m0 = sm.Km[tq];
+                                const double k0 = sm.Kv[tq];
+                                a0 = fma(k0, g_buf[(z - m0) & (P - 1)], a0);
+                                b0 = fma(k0, g_buf[(z1 - m0) & (P - 1)], b0);
+                            }
+                            Lu_out[z] = z < D ? a0 + a1 : 0.0;
+                            if (z1 < Dp) Lu_out[z1] = z1 < D ? b0 + b1 : 0.0;
+                        }
+                    } else {                                     // lib/run.py:675-676
+                        for (int z = lane; z < Dp; z += 32) Lu_out[z] = z < D ? g_buf[z] : 0.0;
+                    }
+                }
+                PH_ADD(13);                                      // [13] A/P profile
+                __threadfence_block();
+                bar_arrive_named(2 + par, cntAll);
+            }
+        }
+        __syncthreads();                           // sweep boundary: bc[2] visible, pipeline drained
+    }
+
+    // write the resident columns back
+    if (roleW && wt && heldX >= 0 && heldX < W) {
+        const int ytop = heldY - pb.fhh;
+        const int lo = max(0, -ytop), n = min(fh, H - ytop) - lo;
+        char* p = (char*)(err + ((long long)ytop * W + heldX) * Dp + zp * VEC);
+#pragma unroll
+        for (int i = 0; i < NE; ++i)
+            if ((unsigned)(i - lo) < (unsigned)n) *(V*)(p + (size_t)i * rstride * sizeof(T)) = ecache[i];
+    }
+    if (roleB && lane == 0) {
+        pb.accepted[chain] = accepted;
+        pb.rate[chain] = rate;
+        pb.iters[chain] = it;
+        if (!alive) pb.active[chain] = 0;
+    }
+}
+
+}  // namespace d3d
