@@ -179,14 +179,10 @@ static void choose_launch(d3d_ctx* c) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         c->use_nc = c->ne != 0 && pb.n_chains > sms;
         if (const char* e = getenv("D3D_ROW_VARIANT")) c->use_nc = c->ne != 0 && atoi(e) == 0;
-        const int nwt_slide = pb.fw * zl;
-        const int ne_s = c->ne == 0 ? 0 : (c->ne > 13 ? 13 : c->ne);
+        const int nwt_slide = (pb.fw + 1) * zl;
         c->slide_threads = ((nwt_slide + 31) / 32) * 32 + 96;
-        // common block + FSF tables per border state + cp.async staging (residual [+ 1/variance])
-        c->slide_smem = c->sweep_smem_base(pb) + (size_t)pb.fh * pb.fh * pb.fw * sizeof(double) +
-                        (size_t)(pb.var_is_cube ? 2 : 1) * pb.fw * ne_s * zl * 16 + 32;
-        c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384 && pb.H >= pb.fh &&
-                       c->slide_smem <= 220 * 1024;
+        c->slide_smem = c->sweep_smem_base(pb);
+        c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384;
         if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);

@@ -5,27 +5,32 @@
 // kernel keeps the whole window of the chain -- residual AND 1/variance -- in
 // registers across sites:
 //
-//   * (fw+1) column groups of ZL = Dp/VEC threads; group r owns the window
-//     column X with X = r (mod fw+1) and keeps its fh rows in registers
-//     (one 16-byte vector per row);
+//   * (fw+1) column groups of ZL = Dp/VEC threads; group r owns the column X with
+//     X = r (mod fw+1) of [x-fhw, x+fhw+1] and keeps its fh rows in registers (one
+//     16-byte vector per row);
 //   * per site only the group whose column left the window writes it back and
-//     loads the column that will ENTER the window at the next site (the window
-//     is fw wide, fw+1 columns are resident), so the load latency overlaps a
-//     whole site update and HBM/L2 traffic drops from 3*fh*fw to ~3*fh vectors
-//     per site (all columns are reloaded when the row changes);
+//     loads the column that will ENTER the window at the next site (the window is
+//     fw wide, fw+1 columns are resident).  HBM/L2 traffic per site drops from
+//     3*fh*fw to ~3*fh vectors (all columns are reloaded when the row changes);
 //   * the sums h[z], G[z] (d3d_kernels.cuh header) and the residual update are
 //     pure register arithmetic.
 //
 // Warp roles (named barriers, PTX bar.sync / bar.arrive):
 //   W  window warps                       sums, partial reduction, update
-//   A  old line profile  Lu(c_old,w_old)  } run up to two sites ahead of the
-//   P  proposal (Philox, Cauchy jump) +   } decisions, double-buffered in smem
-//      new line profile  Lu(c_new,w_new)  }
+//   A  accept uniform + first truncated-normal draws (lane-parallel log/sqrt/cos)
+//      + old line profile Lu(c_old,w_old)   } up to two sites ahead of the decisions,
+//   P  proposal (Philox, Cauchy jump)       } double-buffered in shared memory
+//      + new line profile Lu(c_new,w_new)   }
 //   B  accept test + truncated-normal Gibbs draw
 // Barrier ids: 2,3 READY[parity] (A,P arrive; W,B wait)  4,5 FREE[parity]
 // (W,B arrive two sites later; A,P wait)  6 partials ready (W,B)  7 decision
 // broadcast (W,B).  Look-ahead never crosses a sweep boundary, where the
 // acceptance-rate test of lib/run.py:344-359 needs the finished sweep.
+//
+// Code size matters here: the per-site critical path is a latency-bound chain of a few
+// hundred instructions, and a kernel image beyond the ~32 KB instruction cache triples the
+// cost of every one of them (measured).  Hence rolled loops wherever no register
+// array is indexed, one copy of each libm routine, and cold paths out of line.
 #pragma once
 
 namespace d3d {
@@ -36,7 +41,7 @@ __device__ __forceinline__ void bar_arrive_named(int id, int nthreads) {
 
 // 8 per-lane partial sums -> 8 warp totals with 7 double shuffles (instead of 8 x 5):
 // each round halves the number of slots a lane is responsible for.  On return the
-// lanes with (lane & 3) == 0 hold the total of slot ((lane >> 2) & 7) in `out`.
+// lanes with (lane & 3) == 0 hold the total of slot warp_sum8_slot(lane).
 __device__ __forceinline__ double warp_sum8(const double* v, int lane) {
     double w4[4], w2[2], w1;
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
@@ -59,7 +64,7 @@ __device__ __forceinline__ double warp_sum8(const double* v, int lane) {
     }
     w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
     w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
-    return w1;      // slot index = b4*4 + b3*2 + b2
+    return w1;
 }
 __device__ __forceinline__ int warp_sum8_slot(int lane) {
     return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
@@ -67,8 +72,8 @@ __device__ __forceinline__ int warp_sum8_slot(int lane) {
 
 template <typename T, bool IVCUBE, int NE>
 __global__ void __launch_bounds__(384, 1)
-sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep, double min_rate,
-                       double* chain_out, double* lik_out, long long row_first,
+sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep,
+                       double min_rate, double* chain_out, double* lik_out, long long row_first,
                        long long rows_local) {
     typedef typename Vec<T>::V V;
     const int VEC = Vec<T>::N;
@@ -81,12 +86,12 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
     if (!pb.active[chain]) return;
     load_constants(sm, pb);
     if (threadIdx.x == 0) sm.bc[2] = (double)pb.accepted[chain];
-    __syncthreads();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int Dp = pb.Dp, W = pb.W, H = pb.H, fw = pb.fw, fh = pb.fh;
+    const int Dp = pb.Dp, W = pb.W, H = pb.H, fw = pb.fw, fh = pb.fh, fhh = pb.fhh;
     const int ZL = Dp / VEC;
-    const int nwt = fw * ZL;                       // fw column groups of ZL threads
+    const int ngrp = fw + 1;                       // resident columns: the window + the next one
+    const int nwt = ngrp * ZL;
     const int nww = (nwt + 31) >> 5;
     const bool roleW = warp < nww, roleA = warp == nww, roleP = warp == nww + 1,
                roleB = warp == nww + 2;
@@ -97,38 +102,29 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
     const int ns = pb.n_sites[cube];
     const int* sites = pb.sites + (size_t)cube * pb.max_sites;
     const size_t HW = (size_t)H * W;
-    const size_t rstride = (size_t)W * Dp;
-    T* const err = (T*)pb.err + (size_t)chain * HW * Dp;
-    const T* const ivc = IVCUBE ? (const T*)pb.iv + (size_t)cube * HW * Dp : nullptr;
+    const size_t row_bytes = (size_t)W * Dp * sizeof(T);
+    char* const err = (char*)((T*)pb.err + (size_t)chain * HW * Dp);
+    const char* const ivc =
+        IVCUBE ? (const char*)((const T*)pb.iv + (size_t)cube * HW * Dp) : nullptr;
     const double ivs = IVCUBE ? 0.0 : pb.iv_scalar[cube];
     const double ira = 1.0 / pb.prior_var[cube];
 
-    // Column groups: fw groups of ZL threads, group r owns the window column X = r (mod fw)
-    // and keeps its fh rows (residual, and 1/variance) in registers.  The column that enters
-    // the window at the NEXT site is prefetched with cp.async into a private shared-memory
-    // staging slot, so its latency never blocks the register scoreboard of the warp.
-    V ecache[NE];
-    V ivcache[IVCUBE ? NE : 1];
-#pragma unroll
-    for (int i = 0; i < NE; ++i) { ecache[i] = V(); if (IVCUBE) ivcache[i] = V(); }
-    const int NOCOL = -(1 << 30);
-    int heldX = NOCOL, heldY = NOCOL, pendX = NOCOL, pendY = NOCOL;
-    // shared memory beyond the common block: FSF tables per border state, staging slots
-    double* const Ftab = smem_raw + smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp);
-    V* const stage_e = (V*)(((size_t)(Ftab + (size_t)fh * fh * fw) + 15) & ~(size_t)15) +
-                       ((size_t)grp * NE) * ZL + zp;
-    V* const stage_v = stage_e + (size_t)fw * NE * ZL;
-    // Ftab[s][i][dx] = F[i][dx] with the rows that fall outside the cube zeroed:
-    // s = 0 interior, s = t (1..fhh) t rows clipped at the top, s = fhh + b b rows at the bottom
-    for (int q = tid; q < fh * fh * fw; q += blockDim.x) {
-        const int st = q / (fh * fw), rem = q - st * fh * fw, i = rem / fw;
-        const int top = st <= pb.fhh ? st : 0, bot = st > pb.fhh ? st - pb.fhh : 0;
-        Ftab[q] = (i >= top && i < fh - bot) ? sm.F[rem] : 0.0;
-    }
     __syncthreads();
 
+    // register-resident column of this thread: rows y-fhh .. y-fhh+fh-1 of column heldX.
+    // fw+1 column groups: group r owns the column X = r (mod fw+1) of [x-fhw, x+fhw+1]; the
+    // extra column is the one that enters the window at the next site, so its loads (issued
+    // when the group's previous column leaves) have a whole site update to complete.
+    V ecache[NE];
+    V ivcache[IVCUBE ? NE : 1];
+    const int NOCOL = -(1 << 30);
+    int heldX = NOCOL, heldY = NOCOL;
+    const size_t rstride = (size_t)W * Dp;
+    T* const errT = (T*)err;
+    const T* const ivT = (const T*)ivc;
+
     double rate = pb.rate[chain];
-    long long accepted = pb.accepted[chain];       // owned by warp B
+    long long accepted = pb.accepted[chain];       // owned by lane 0 of warp B
     long long it = it0;
     int alive = 1;
 
@@ -155,92 +151,50 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
 
             PH_T0();
             if (roleW) {
-                // ---- make the resident column of this thread current for (y, x) ---------
-                const int top = max(0, pb.fhh - y), bot = max(0, y + pb.fhh - (H - 1));
-                const double* ftab = Ftab + (top ? top : (bot ? pb.fhh + bot : 0)) * fh * fw;
+                // ---- make the resident columns current for (y, x) --------------------
                 const int xl = x - pb.fhw;
-                int m = (grp - xl) % fw;
-                if (m < 0) m += fw;
-                const int Xn = xl + m;                           // the window column = grp (mod fw)
+                int m = (grp - xl) % ngrp;
+                if (m < 0) m += ngrp;
+                const int Xn = xl + m;                           // column of this group
                 if (wt && (Xn != heldX || y != heldY)) {
-                    if (heldX >= 0 && heldX < W) {               // old column back to memory
-                        const int ytop = heldY - pb.fhh;
-                        const int lo = max(0, -ytop), n = min(fh, H - ytop) - lo;
-                        char* p = (char*)(err + ((long long)ytop * W + heldX) * Dp + zp * VEC);
+                    const int ytop_old = heldY - fhh;
+                    if (heldX >= 0 && heldX < W && heldY != NOCOL) {       // write back
+                        T* p = errT + ((size_t)max(ytop_old, 0) * W + heldX) * Dp + zp * VEC;
 #pragma unroll
-                        for (int i = 0; i < NE; ++i)
-                            if ((unsigned)(i - lo) < (unsigned)n)
-                                *(V*)(p + (size_t)i * rstride * sizeof(T)) = ecache[i];
+                        for (int i = 0; i < NE; ++i) {
+                            const int Y = ytop_old + i;
+                            if (i < fh && Y >= 0 && Y < H) { *(V*)p = ecache[i]; p += rstride; }
+                        }
                     }
+                    const int ytop = y - fhh;
                     if (Xn >= 0 && Xn < W) {
-                        const int ytop = y - pb.fhh;
-                        const int lo = top, n = fh - bot - top;
-                        if (pendX == Xn && pendY == y) {         // prefetched at the previous site
-                            asm volatile("cp.async.wait_all;" ::: "memory");
+                        const size_t off = ((size_t)max(ytop, 0) * W + Xn) * Dp + zp * VEC;
+                        const T* p = errT + off;
+                        const T* q = IVCUBE ? ivT + off : nullptr;
 #pragma unroll
-                            for (int i = 0; i < NE; ++i)
-                                if ((unsigned)(i - lo) < (unsigned)n) {
-                                    ecache[i] = stage_e[i * ZL];
-                                    if (IVCUBE) ivcache[i] = stage_v[i * ZL];
-                                }
-                        } else {                                 // first site of a launch / jumps
-                            const long long off = ((long long)ytop * W + Xn) * Dp + zp * VEC;
-                            const char* p = (const char*)(err + off);
-                            const char* q = IVCUBE ? (const char*)(ivc + off) : nullptr;
-#pragma unroll
-                            for (int i = 0; i < NE; ++i)
-                                if ((unsigned)(i - lo) < (unsigned)n) {
-                                    ecache[i] = *(const V*)(p + (size_t)i * rstride * sizeof(T));
-                                    if (IVCUBE)
-                                        ivcache[i] = *(const V*)(q + (size_t)i * rstride * sizeof(T));
-                                }
+                        for (int i = 0; i < NE; ++i) {
+                            const int Y = ytop + i;
+                            if (i < fh && Y >= 0 && Y < H) {
+                                ecache[i] = *(const V*)p; p += rstride;
+                                if (IVCUBE) { ivcache[i] = *(const V*)q; q += rstride; }
+                            } else {
+                                ecache[i] = V();
+                                if (IVCUBE) ivcache[i] = V();
+                            }
                         }
                     }
                     heldX = Xn; heldY = y;
                 }
-                // ---- prefetch the column this thread will need at the next site ----------
-                if (wt && j + 1 < ns) {
-                    const int site2 = sites[j + 1];
-                    const int y2 = site2 / W, x2 = site2 - y2 * W;
-                    const int xl2 = x2 - pb.fhw;
-                    int m2 = (grp - xl2) % fw;
-                    if (m2 < 0) m2 += fw;
-                    const int X2 = xl2 + m2;
-                    // (same column on another row is still dirty in registers: no prefetch)
-                    if (X2 != heldX && X2 >= 0 && X2 < W) {
-                        const int ytop = y2 - pb.fhh;
-                        const int lo = max(0, -ytop), n = min(fh, H - ytop) - lo;
-                        const long long off = ((long long)ytop * W + X2) * Dp + zp * VEC;
-                        const char* p = (const char*)(err + off);
-                        const char* q = IVCUBE ? (const char*)(ivc + off) : nullptr;
-                        const unsigned se = (unsigned)__cvta_generic_to_shared(stage_e);
-                        const unsigned sv = (unsigned)__cvta_generic_to_shared(stage_v);
-#pragma unroll
-                        for (int i = 0; i < NE; ++i)
-                            if ((unsigned)(i - lo) < (unsigned)n) {
-                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                                                 se + (unsigned)(i * ZL * 16)),
-                                             "l"(p + (size_t)i * rstride * sizeof(T))
-                                             : "memory");
-                                if (IVCUBE)
-                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
-                                                     sv + (unsigned)(i * ZL * 16)),
-                                                 "l"(q + (size_t)i * rstride * sizeof(T))
-                                                 : "memory");
-                            }
-                        pendX = X2; pendY = y2;
-                    }
-                }
-                // ---- window sums (registers only; clipped rows have F = 0 in ftab) --------
-                const int dx = heldX - xl;
-                const bool active = wt && heldX >= 0 && heldX < W;   // dx in [0, fw) by construction
+                // ---- window sums (registers only) -------------------------------------
+                const int dx = heldX - xl;                       // FSF column, valid if active
+                const bool active = wt && dx >= 0 && dx < fw && heldX >= 0 && heldX < W;
                 double part[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) part[k] = 0.0;
                 double h[VEC], g[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
-                const double* fcol = ftab + (active ? dx : 0);
+                const double* fcol = sm.F + (active ? dx : 0);
                 if (active) {
                     double f2 = 0.0;
 #pragma unroll
@@ -259,9 +213,12 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                                     g[v] = fma(ff, w_[v], g[v]);
                                 }
                             } else {
+                                // rows outside the cube hold e = 0 but must not count in F^2
+                                const int Y = y - fhh + i;
+                                const double fin = (Y >= 0 && Y < H) ? f : 0.0;
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) h[v] = fma(f, e[v], h[v]);
-                                f2 = fma(f, f, f2);
+                                f2 = fma(fin, fin, f2);
                             }
                         }
                     }
@@ -270,7 +227,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                         for (int v = 0; v < VEC; ++v) { h[v] *= ivs; g[v] = ivs * f2; }
                     }
                 }
-                if (warp == 0) PH_ADD(0);                        // [0] W columns + sums
+                if (warp == 0) PH_ADD(0);                        // [0] W switch + sums
                 bar_sync_named(2 + par, cntAll);                 // READY: profiles of site j
                 if (warp == 0) PH_ADD(1);                        // [1] W wait READY
                 double lo_v[VEC], ln_v[VEC];
@@ -294,7 +251,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                 }
                 if (warp == 0) PH_ADD(2);                        // [2] W partials
                 bar_sync_named(6, cntWB);                        // partials visible to B
-                if (warp == 0) PH_ADD(3);                        // [3] W wait bar6
+                if (warp == 0) PH_ADD(3);                        // [3] W housekeeping
                 bar_sync_named(7, cntWB);                        // decision broadcast
                 if (warp == 0) PH_ADD(4);                        // [4] W wait decision
                 if (active) {
@@ -306,7 +263,8 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                         coef[v] = a * lo_v[v] - r * (acc ? ln_v[v] : lo_v[v]);
 #pragma unroll
                     for (int i = 0; i < NE; ++i) {
-                        if (i < fh) {                            // F = 0 on clipped rows: no-op there
+                        const int Y = y - fhh + i;
+                        if (i < fh && Y >= 0 && Y < H) {         // keep the zero padding rows zero
                             const double f = fcol[i * fw];
                             double e[VEC];
                             unpack(ecache[i], e);
@@ -359,7 +317,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                 const double mu = S1 * (sg * sg);
                 const double lo = pb.pmin[cube * 3], hi = pb.pmax[cube * 3];
                 const double as = (lo - mu) * isg, bs = (hi - mu) * isg;   // lib/rtnorm.py:74-76
-                double rs;
+                double rs = 0.0;
                 int fail = 0;
                 bool done = false;
                 const bool plain = (as < bs) && !(fabs(as) > fabs(bs));   // no mirror (:108)
@@ -387,7 +345,10 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                     if (fail) atomicExch(pb.status, 1);
                     double* prm = pb.params + ((size_t)chain * HW + site) * 3;
                     prm[0] = r; prm[1] = c_end; prm[2] = w_end;                 // :448,:499,:516
-                    if (crow) { double* cr = crow + (size_t)site * 3; cr[0] = r; cr[1] = c_end; cr[2] = w_end; }
+                    if (crow) {
+                        double* cr = crow + (size_t)site * 3;
+                        cr[0] = r; cr[1] = c_end; cr[2] = w_end;
+                    }
                     if (lrow) lrow[site] = delta;                               // :430-432
                     sm.bc[0] = acc ? 1.0 : 0.0;
                     sm.bc[1] = r;
@@ -467,37 +428,25 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
                 {
                     const double inv2w2 = 1.0 / (2.0 * (w_prof * w_prof));
                     const int D = pb.D, P = pb.P;
-                    for (int z = lane; z < Dp; z += 64) {
-                        const int z1 = z + 32;
-                        const double d0 = (double)z - c_prof, d1 = (double)z1 - c_prof;
-                        const double g0 = exp(-1.0 * (d0 * d0) * inv2w2);
-                        const double g1 = exp(-1.0 * (d1 * d1) * inv2w2);
-                        if (z < D) g_buf[z] = g0;
-                        if (z1 < D) g_buf[z1] = g1;
+#pragma unroll 1
+                    for (int z = lane; z < D; z += 32) {
+                        const double d0 = (double)z - c_prof;
+                        g_buf[z] = exp(-1.0 * (d0 * d0) * inv2w2);
                     }
                     __syncwarp();
                     if (pb.has_lsf) {
                         const int nt = pb.ntaps;
-                        for (int z = lane; z < Dp; z += 64) {
-                            const int z1 = z + 32;
-                            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 1
+                        for (int z = lane; z < Dp; z += 32) {
+                            double a0 = 0.0, a1 = 0.0;
                             int tq = 0;
+#pragma unroll 1
                             for (; tq + 1 < nt; tq += 2) {
-                                const int m0 = sm.Km[tq], m1 = sm.Km[tq + 1];
-                                const double k0 = sm.Kv[tq], k1 = sm.Kv[tq + 1];
-                                a0 = fma(k0, g_buf[(z - m0) & (P - 1)], a0);
-                                a1 = fma(k1, g_buf[(z - m1) & (P - 1)], a1);
-                                b0 = fma(k0, g_buf[(z1 - m0) & (P - 1)], b0);
-                                b1 = fma(k1, g_buf[(z1 - m1) & (P - 1)], b1);
+                                a0 = fma(sm.Kv[tq], g_buf[(z - sm.Km[tq]) & (P - 1)], a0);
+                                a1 = fma(sm.Kv[tq + 1], g_buf[(z - sm.Km[tq + 1]) & (P - 1)], a1);
                             }
-                            if (tq < nt) {
-                                const int m0 = sm.Km[tq];
-                                const double k0 = sm.Kv[tq];
-                                a0 = fma(k0, g_buf[(z - m0) & (P - 1)], a0);
-                                b0 = fma(k0, g_buf[(z1 - m0) & (P - 1)], b0);
-                            }
+                            if (tq < nt) a0 = fma(sm.Kv[tq], g_buf[(z - sm.Km[tq]) & (P - 1)], a0);
                             Lu_out[z] = z < D ? a0 + a1 : 0.0;
-                            if (z1 < Dp) Lu_out[z1] = z1 < D ? b0 + b1 : 0.0;
                         }
                     } else {                                     // lib/run.py:675-676
                         for (int z = lane; z < Dp; z += 32) Lu_out[z] = z < D ? g_buf[z] : 0.0;
@@ -511,14 +460,15 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
         __syncthreads();                           // sweep boundary: bc[2] visible, pipeline drained
     }
 
-    // write the resident columns back
-    if (roleW && wt && heldX >= 0 && heldX < W) {
-        const int ytop = heldY - pb.fhh;
-        const int lo = max(0, -ytop), n = min(fh, H - ytop) - lo;
-        char* p = (char*)(err + ((long long)ytop * W + heldX) * Dp + zp * VEC);
+    // ---- write the resident columns back ----------------------------------------------------
+    if (roleW && wt && heldX >= 0 && heldX < W && heldY != NOCOL) {
+        const int ytop_old = heldY - fhh;
+        T* p = errT + ((size_t)max(ytop_old, 0) * W + heldX) * Dp + zp * VEC;
 #pragma unroll
-        for (int i = 0; i < NE; ++i)
-            if ((unsigned)(i - lo) < (unsigned)n) *(V*)(p + (size_t)i * rstride * sizeof(T)) = ecache[i];
+        for (int i = 0; i < NE; ++i) {
+            const int Y = ytop_old + i;
+            if (i < fh && Y >= 0 && Y < H) { *(V*)p = ecache[i]; p += rstride; }
+        }
     }
     if (roleB && lane == 0) {
         pb.accepted[chain] = accepted;
