@@ -78,8 +78,8 @@ def load():
     lib.d3d_get_params.argtypes = [vp, vp]
     lib.d3d_init_params_uniform.argtypes = [vp]
     lib.d3d_forward.argtypes = [vp, vp, ci, vp]
-    lib.d3d_simulate.argtypes = [vp, vp, vp]
-    lib.d3d_simulate_clean.argtypes = [vp, vp, vp]
+    lib.d3d_simulate.argtypes = [vp, vp, ci, vp]
+    lib.d3d_simulate_clean.argtypes = [vp, vp, ci, vp]
     lib.d3d_get_residual.argtypes = [vp, vp]
     lib.d3d_conv1d.argtypes = [vp, vp, ci, ci, vp, vp]
     lib.d3d_rtnorm.argtypes = [vp, ci, vp, vp, vp, vp, u64, u32, u32, vp, vp]
@@ -202,17 +202,18 @@ class Context(object):
         return sim, chi2
 
     def simulate(self, params):
+        """params [n, H, W, 3] (n <= n_chains) -> convolved cubes [n, D, H, W]."""
         D, H, W = self.shape
-        params = _f64(params).reshape(self.n_chains, H, W, 3)
-        sim = np.empty((self.n_chains, D, H, W))
-        _check(self.lib.d3d_simulate(self.h, _ptr(params), _ptr(sim)))
+        params = _f64(params).reshape(-1, H, W, 3)
+        sim = np.empty((params.shape[0], D, H, W))
+        _check(self.lib.d3d_simulate(self.h, _ptr(params), params.shape[0], _ptr(sim)))
         return sim
 
     def simulate_clean(self, params):
         D, H, W = self.shape
-        params = _f64(params).reshape(self.n_chains, H, W, 3)
-        sim = np.empty((self.n_chains, D, H, W))
-        _check(self.lib.d3d_simulate_clean(self.h, _ptr(params), _ptr(sim)))
+        params = _f64(params).reshape(-1, H, W, 3)
+        sim = np.empty((params.shape[0], D, H, W))
+        _check(self.lib.d3d_simulate_clean(self.h, _ptr(params), params.shape[0], _ptr(sim)))
         return sim
 
     def get_residual(self):

@@ -55,6 +55,7 @@ struct d3d_ctx {
     int generic_threads = 256;
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
     static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
+    void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
     bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
@@ -113,6 +114,7 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_problem(c);
+    if (c->d_sched) cudaFree(c->d_sched);
     if (c->rt_x) cudaFree(c->rt_x);
     if (c->rt_yu) cudaFree(c->rt_yu);
     if (c->rt_nc) cudaFree(c->rt_nc);
@@ -452,8 +454,9 @@ static int stencil_config(const d3d_ctx* c, int* TY, int* TX, int* ZC, size_t* s
 
 
 static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double* sim_dev,
-                       int write_err, double* chi2_dev) {
-    const Problem& pb = c->pb;
+                       int write_err, double* chi2_dev, int n_sets = -1) {
+    Problem pb = c->pb;
+    if (n_sets > 0) pb.n_chains = n_sets;        // explicit parameter sets (first n_sets chain slots)
     const size_t HW = (size_t)pb.H * pb.W;
     {
         const int threads = 256, wpb = threads / 32;
@@ -482,8 +485,9 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
 }
 
 static int forward_common(d3d_ctx* c, const double* params_any, int convolve, double* sim_out,
-                          int write_err, double* chi2_out) {
-    const Problem& pb = c->pb;
+                          int write_err, double* chi2_out, int n_sets = -1) {
+    Problem pb = c->pb;
+    if (n_sets > 0) pb.n_chains = n_sets;
     CK(cudaSetDevice(c->device));
     const size_t HW = (size_t)pb.H * pb.W;
     const size_t sim_cnt = (size_t)pb.n_chains * pb.D * HW;
@@ -503,7 +507,7 @@ static int forward_common(d3d_ctx* c, const double* params_any, int convolve, do
         if (e != cudaSuccess) rc = fail(D3D_ENOMEM, "cudaMalloc chi2 failed");
         else cudaMemsetAsync(d_chi, 0, pb.n_chains * sizeof(double), c->stream);
     }
-    if (!rc) rc = run_forward(c, d_params, convolve, d_sim, write_err, d_chi);
+    if (!rc) rc = run_forward(c, d_params, convolve, d_sim, write_err, d_chi, n_sets);
     if (!rc && sim_out) {
         cudaError_t e = cudaMemcpyAsync(sim_out, d_sim, sim_cnt * sizeof(double), cudaMemcpyDefault, c->stream);
         if (e != cudaSuccess) rc = fail(D3D_ECUDA, "sim copy failed: %s", cudaGetErrorString(e));
@@ -526,18 +530,23 @@ extern "C" int d3d_forward(d3d_ctx* c, double* sim_out, int write_err, double* c
     return forward_common(c, nullptr, 1, sim_out, write_err, chi2_out);
 }
 
-extern "C" int d3d_simulate(d3d_ctx* c, const double* params, double* sim_out) {
+extern "C" int d3d_simulate(d3d_ctx* c, const double* params, int n_sets, double* sim_out) {
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_simulate before d3d_set_problem");
     if (!params || !sim_out) return fail(D3D_EINVAL, "NULL argument");
-    return forward_common(c, params, 1, sim_out, 0, nullptr);
+    if (n_sets < 1 || n_sets > c->pb.n_chains)
+        return fail(D3D_EINVAL, "d3d_simulate: n_sets must be in [1, n_chains]");
+    return forward_common(c, params, 1, sim_out, 0, nullptr, n_sets);
 }
 
 
-extern "C" int d3d_simulate_clean(d3d_ctx* c, const double* params, double* sim_out) {
+extern "C" int d3d_simulate_clean(d3d_ctx* c, const double* params, int n_sets, double* sim_out) {
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_simulate_clean before d3d_set_problem");
     if (!params || !sim_out) return fail(D3D_EINVAL, "NULL argument");
+    if (n_sets < 1 || n_sets > c->pb.n_chains)
+        return fail(D3D_EINVAL, "d3d_simulate_clean: n_sets must be in [1, n_chains]");
     CK(cudaSetDevice(c->device));
-    const Problem& pb = c->pb;
+    Problem pb = c->pb;
+    pb.n_chains = n_sets;
     const size_t HW = (size_t)pb.H * pb.W;
     size_t total = (size_t)pb.n_chains * pb.D * HW;
     double *d_p = nullptr, *d_o = nullptr;
@@ -683,8 +692,61 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
         const int ne = NE ? NE : 7;
         cudaFuncSetAttribute(sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slide_smem);
-        sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<c->pb.n_chains, c->slide_threads, c->slide_smem, c->stream>>>(
-            c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
+        // balance chains over the SMs (McNaughton wrap-around of the chain x sweep rectangle)
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const int C = c->pb.n_chains;
+        const long long S = it1 - it0;
+        if (C > sms && S > 0 && !getenv("D3D_NO_BALANCE")) {
+            const int G = sms;
+            const long long Tslots = (C * S + G - 1) / G;       // sweeps per CTA
+            std::vector<std::vector<int4>> lists(G);
+            int g = 0; long long used = 0;
+            for (int ch = 0; ch < C; ++ch) {
+                long long room = Tslots - used;
+                if (room >= S) {                                // whole chain on CTA g
+                    lists[g].push_back(make_int4(ch, 0, (int)S, 0));
+                    used += S;
+                    if (used == Tslots && g + 1 < G) { ++g; used = 0; }
+                } else {
+                    // split: the LATE slots of CTA g take the chain's last `room` sweeps, the
+                    // EARLY slots of CTA g+1 its first S-room sweeps
+                    if (room > 0) lists[g].push_back(make_int4(ch, (int)(S - room), (int)S, 0));
+                    ++g; used = 0;
+                    lists[g].insert(lists[g].begin(), make_int4(ch, 0, (int)(S - room), 0));
+                    used = S - room;
+                }
+            }
+            int max_items = 1;
+            for (auto& l : lists) max_items = std::max(max_items, (int)l.size());
+            std::vector<int4> flat((size_t)G * max_items, make_int4(0, 0, 0, 0));
+            std::vector<int> cnt(G);
+            for (int q = 0; q < G; ++q) {
+                cnt[q] = (int)lists[q].size();
+                for (size_t k = 0; k < lists[q].size(); ++k) flat[(size_t)q * max_items + k] = lists[q][k];
+            }
+            std::vector<long long> prog(C, it0);
+            if (c->sched_cap < flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long)) {
+                if (c->d_sched) cudaFree(c->d_sched);
+                c->sched_cap = 2 * (flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long));
+                if (cudaMalloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; return cudaErrorMemoryAllocation; }
+            }
+            char* base = (char*)c->d_sched;
+            int4* d_items = (int4*)base;
+            long long* d_prog = (long long*)(base + flat.size() * sizeof(int4));
+            int* d_cnt = (int*)(base + flat.size() * sizeof(int4) + C * sizeof(long long));
+            cudaMemcpyAsync(d_items, flat.data(), flat.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream);
+            cudaMemcpyAsync(d_prog, prog.data(), C * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+            cudaMemcpyAsync(d_cnt, cnt.data(), G * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+            cudaStreamSynchronize(c->stream);       // host vectors go out of scope
+            sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<G, c->slide_threads, c->slide_smem, c->stream>>>(
+                c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local,
+                d_items, d_cnt, max_items, d_prog);
+        } else {
+            sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<C, c->slide_threads, c->slide_smem, c->stream>>>(
+                c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local,
+                nullptr, nullptr, 0, nullptr);
+        }
     } else if (NE != 0 && c->use_nc) {
         cudaFuncSetAttribute(sweep_seq_nc_kernel<T, IV>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);

@@ -72,19 +72,40 @@ __device__ __forceinline__ int warp_sum8_slot(int lane) {
 
 template <typename T, bool IVCUBE, int NE>
 __global__ void __launch_bounds__(384, 1)
-sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long long it1, int keep,
-                       double min_rate, double* chain_out, double* lik_out, long long row_first,
-                       long long rows_local) {
+sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, long long it1_all,
+                       int keep, double min_rate, double* chain_out, double* lik_out,
+                       long long row_first, long long rows_local, const int4* items,
+                       const int* item_count, int max_items, volatile long long* progress) {
     typedef typename Vec<T>::V V;
     const int VEC = Vec<T>::N;
     extern __shared__ double smem_raw[];
     Smem sm;
     carve(sm, smem_raw, pb);
-    const int chain = blockIdx.x;
-    if (chain >= pb.n_chains) return;
-    const int cube = chain / pb.chains_per_cube;
-    if (!pb.active[chain]) return;
     load_constants(sm, pb);
+    // Work items (chain, first iteration, end iteration) of this CTA.  With more chains than
+    // SMs the host lays the chain x sweep rectangle over the CTAs by McNaughton's wrap-around
+    // rule, so that every SM gets the same number of sweeps; a chain split over two CTAs is
+    // handed over through `progress` (both CTAs are resident: grid <= number of SMs).
+    const int n_items = items ? item_count[blockIdx.x] : 1;
+  for (int item = 0; item < n_items; ++item) {
+    int chain; long long it0, it1;
+    if (items) {
+        const int4 w = items[(size_t)blockIdx.x * max_items + item];
+        chain = w.x; it0 = it0_all + w.y; it1 = it0_all + w.z;
+        if (threadIdx.x == 0) while (progress[chain] < it0) __nanosleep(200);
+        __syncthreads();
+        __threadfence();
+    } else {
+        chain = blockIdx.x; it0 = it0_all; it1 = it1_all;
+        if (chain >= pb.n_chains) return;
+    }
+    const int cube = chain / pb.chains_per_cube;
+    if (!pb.active[chain]) {                       // chain stopped earlier (acceptance rate)
+        __syncthreads();
+        if (items && threadIdx.x == 0) progress[chain] = it1;
+        continue;
+    }
+    __syncthreads();                               // previous item fully retired
     if (threadIdx.x == 0) sm.bc[2] = (double)pb.accepted[chain];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -476,6 +497,12 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0, long l
         pb.iters[chain] = it;
         if (!alive) pb.active[chain] = 0;
     }
+    if (items) {                                   // hand the chain over to its next owner
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) progress[chain] = it1;
+    }
+  }
 }
 
 }  // namespace d3d

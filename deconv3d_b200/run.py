@@ -319,19 +319,15 @@ class Run(object):
 
     # -- simulators (GPU) ----------------------------------------------------------------------
 
-    def _tiled_params(self, parameters):
-        p = np.asarray(parameters, dtype=np.float64)
-        return np.ascontiguousarray(np.broadcast_to(p, (self._ctx.n_chains,) + p.shape))
-
     def simulate_clean(self, shape, parameters):
         """Cube of the un-convolved lines (lib/run.py:597-621)."""
         self._check_shape(shape)
-        return self._ctx.simulate_clean(self._tiled_params(parameters))[0]
+        return self._ctx.simulate_clean(np.asarray(parameters, dtype=np.float64)[None])[0]
 
     def simulate_convolved(self, shape, parameters):
         """Cube of the lines convolved by the LSF and the FSF (lib/run.py:623-652)."""
         self._check_shape(shape)
-        return self._ctx.simulate(self._tiled_params(parameters))[0]
+        return self._ctx.simulate(np.asarray(parameters, dtype=np.float64)[None])[0]
 
     def _check_shape(self, shape):
         if tuple(shape) != tuple(self.cube.data.shape):

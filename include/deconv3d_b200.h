@@ -121,11 +121,12 @@ int d3d_init_params_uniform(d3d_ctx* ctx);
  *   write_err non-zero: residual <- data - sim (lib/run.py:334, 525-534)
  *   chi2_out  [n_chains] float64 or NULL: 0.5*sum(err^2/var) over the cube     */
 int d3d_forward(d3d_ctx* ctx, double* sim_out, int write_err, double* chi2_out);
-/* Same, for explicit parameters that are not the chain state (used by
- * Run.simulate_convolved(shape, parameters)); never touches the residual. */
-int d3d_simulate(d3d_ctx* ctx, const double* params, double* sim_out);
+/* Same, for n_sets explicit parameter maps [n_sets][H][W][3] that are not the chain
+ * state (Run.simulate_convolved(shape, parameters)); set k uses the cube of chain slot k.
+ * Never touches the residual.  sim_out: [n_sets][D][H][W]. */
+int d3d_simulate(d3d_ctx* ctx, const double* params, int n_sets, double* sim_out);
 /* Un-convolved lines, Run.simulate_clean (lib/run.py:597-621). */
-int d3d_simulate_clean(d3d_ctx* ctx, const double* params, double* sim_out);
+int d3d_simulate_clean(d3d_ctx* ctx, const double* params, int n_sets, double* sim_out);
 /* Current residual err_old as [n_chains][D][H][W] float64 (lib/run.py:334). */
 int d3d_get_residual(d3d_ctx* ctx, double* err_out);
 

@@ -400,3 +400,32 @@ def test_multi_cube_galaxies(nat):
         ch = np.zeros((2, 4, H, W, 3))
         c1.sweep(1, 3, chain_out=ch)
         assert np.array_equal(ch[:, 1:], chain[2 * i:2 * i + 2, 1:])
+
+
+def test_balanced_schedule_more_chains_than_sms(nat):
+    """More chains than SMs: the chain x sweep rectangle is laid over the SMs by the
+    wrap-around rule and some chains are handed from one CTA to another mid-call.  Every
+    chain must still equal its own single-chain run bit for bit."""
+    g = load_golden('ref_run_A')
+    data, fsf, lsf = g['data'], g['fsf'], g['lsf']
+    var = np.array([0.01])
+    n = 333
+    ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=n, seed=5)
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+    chain = np.zeros((n, 8, 9, 10, 3))
+    acc, its, _ = ctx.sweep(1, 7, chain_out=chain)
+    assert (its == 8).all()
+    res = ctx.get_residual()
+    for k in (0, 1, 147, 148, 149, 200, 332):
+        c1, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=1, seed=5, first_chain=k)
+        c1.init_params_uniform()
+        c1.forward(write_err=True)
+        ch = np.zeros((1, 8, 9, 10, 3))
+        a1, _, _ = c1.sweep(1, 7, chain_out=ch)
+        assert np.array_equal(ch[0, 1:], chain[k, 1:]), k
+        assert a1[0] == acc[k]
+        assert np.array_equal(c1.get_residual()[0], res[k])
+    # a second call continues every chain where it stopped
+    acc2, its2, _ = ctx.sweep(8, 3)
+    assert (its2 == 11).all() and (acc2 >= acc).all()
