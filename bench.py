@@ -146,6 +146,22 @@ class ClockSampler(object):
                 'power_w_max': max(float(s[2]) for s in self.samples)}
 
 
+def measured_traffic(workload, chains, sweeps, dtype, mode):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/*_traffic.json), only when it was taken on the same workload."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')), reverse=True):
+        try:
+            t = json.load(open(path))
+            m = t.get('match', {})
+            if (m.get('workload') == workload and m.get('chains') == chains and
+                    m.get('sweeps') == sweeps and m.get('dtype') == dtype and m.get('mode') == mode):
+                return float(t['dram_bytes_per_launch']), os.path.relpath(path, ROOT)
+        except Exception:               # noqa: BLE001
+            continue
+    return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -346,6 +362,7 @@ def main():
         return
 
     peak, peak_src = measured_peak()
+    traffic, traffic_src = measured_traffic(args.workload, n_chains, sweeps, args.dtype, args.mode)
     kern_total_ms = float(np.sum(kern_ms))
     achieved = bytes_algo / (kern_total_ms * 1e-3) / 1e9
     state_mb = n_chains * D * H * W * (8 if args.dtype == 'f64' else 4) / 1e6
@@ -363,13 +380,16 @@ def main():
         'clocks': clocks.summary(),
         'roofline': {
             'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-            'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
-            'kernel': 'sweep_seq_kernel' if args.mode == 'sequential' else 'sweep_colour_kernel',
+            'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+            'peak_source': peak_src,
+            'kernel': 'sweep_seq_slide_kernel' if args.mode == 'sequential' else 'sweep_colour_kernel',
             'algorithmic_bytes_per_launch': bytes_algo / max(1, args.steps),
             'kernel_ms_per_launch': kern_total_ms / max(1, args.steps),
-            'note': 'algorithmic bytes = (3 with a variance cube | 2 with a scalar variance) * s * D * '
-                    'sum_sites wh*ww per chain per sweep (SURVEY.md 8d); consecutive windows of a '
-                    'chain overlap, so cache hits can push this above the HBM peak',
+            'note': 'achieved = algorithmic bytes / kernel time; algorithmic bytes = (3 with a variance '
+                    'cube | 2 with a scalar variance) * s * D * sum_sites wh*ww per chain per sweep '
+                    '(SURVEY.md 8d). The sliding register window re-uses 12 of 13 window columns, so '
+                    'real DRAM traffic (traffic, bytes per launch) is ~300x lower and the kernel is '
+                    'latency-bound, see profiles/r01_notes.md',
         },
     }
     if e2e is not None:
