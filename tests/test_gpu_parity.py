@@ -429,3 +429,75 @@ def test_balanced_schedule_more_chains_than_sms(nat):
     # a second call continues every chain where it stopped
     acc2, its2, _ = ctx.sweep(8, 3)
     assert (its2 == 11).all() and (acc2 >= acc).all()
+
+
+def _cfg2_problem(nat, chains, dtype=None, fsf_size=13, seed=42):
+    """BASELINE cfg2 at full size: 40x40x40 cube, Moffat 13x13, MUSE LSF, variance cube."""
+    from deconv3d_b200 import synthetic, MUSE
+    D = H = W = 40
+    inst = synthetic.muse_wfm_instrument('moffat', fsf_size)
+    cube0 = MUSE().build_cube(np.zeros((D, H, W)))
+    fsf = np.asarray(inst.fsf.as_image(cube0))
+    lsf = inst.lsf.as_vector(cube0)
+    truth = synthetic.halpha_truth(D, H, W)
+    tmp = nat.Context(0, nat.F64)
+    tmp.set_problem(np.ones((D, H, W)), np.ones(1), fsf, lsf, np.zeros(3), [100., D - 1, D],
+                    [0, .1, .1], 1.0)
+    data = tmp.simulate(truth[None])[0] + synthetic.noise((D, H, W), 0.05, 1234)
+    tmp.close()
+    var = np.full(data.shape, 0.05 ** 2)
+    ctx, pmin, pmax = make_ctx(nat, data, var, fsf, lsf, chains=chains, dtype=dtype, seed=seed)
+    return ctx, data, var, fsf, lsf, truth
+
+
+def test_full_size_cfg2_invariants(nat):
+    """Size-independent properties at BASELINE's full cfg2 size (the oracle needs ~1 ms per
+    proposal there): (1) the incrementally updated residual equals data - forward(parameters)
+    after many sweeps (the drift the reference squashes every 1000 iterations,
+    lib/run.py:521-534, stays at rounding level); (2) chi^2 falls to ~N/2 from a poor start."""
+    ctx, data, var, fsf, lsf, truth = _cfg2_problem(nat, chains=3)
+    rs = np.random.RandomState(0)
+    start = truth * np.array([0.3, 1.0, 1.5]) + np.array([0.0, 1.5, 0.0]) * rs.randn(40, 40, 1)
+    ctx.set_params(np.broadcast_to(start, (3, 40, 40, 3)).copy())
+    _, chi0 = ctx.forward(write_err=True, want_chi2=True)
+    n_it = 400
+    chain = np.zeros((3, n_it // 20 + 1, 40, 40, 3))
+    acc, its, ms = ctx.sweep(1, n_it, keep_one_in=20, refresh_every=0, chain_out=chain)
+    assert (its == n_it + 1).all()
+    res_inc = ctx.get_residual()
+    _, chi1 = ctx.forward(write_err=True, want_chi2=True)
+    res_fresh = ctx.get_residual()
+    assert np.abs(res_inc - res_fresh).max() < 1e-9 * np.abs(data).max()
+    n_vox = data.size
+    assert (chi0 > 5 * n_vox).all()
+    assert (np.abs(2 * chi1 / n_vox - 1.0) < 0.1).all(), chi1 / n_vox
+    # (individual spaxel parameters are ill-constrained by construction -- the PSF mixes
+    # neighbours -- so no per-spaxel recovery is asserted; chi^2 of the convolved model is)
+    assert np.isfinite(chain).all() and (acc > 0).all()
+
+
+def test_full_size_cfg2_float32_storage(nat):
+    ctx, data, var, fsf, lsf, truth = _cfg2_problem(nat, chains=2, dtype=nat.F32)
+    start = truth * np.array([0.3, 1.0, 1.5]) + np.array([0.0, 1.0, 0.0])
+    ctx.set_params(np.broadcast_to(start, (2, 40, 40, 3)).copy())
+    ctx.forward(write_err=True)
+    ctx.sweep(1, 200, refresh_every=100)
+    res_inc = ctx.get_residual()
+    _, chi = ctx.forward(write_err=True, want_chi2=True)
+    assert np.abs(res_inc - ctx.get_residual()).max() < 2e-4 * np.abs(data).max()
+    assert (np.abs(2 * chi / data.size - 1.0) < 0.1).all()
+
+
+@pytest.mark.parametrize('mode', ['seq', 'colour'])
+def test_large_fsf_generic_kernels_vs_oracle(nat, mode):
+    """FSF larger than the row-mapped kernels take (23x23 on a 14x15 field: every window is
+    clipped): the generic kernels against the oracle, decisions included."""
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(3)
+    D, H, W = 10, 14, 15
+    data = synthetic(D, H, W, 9)
+    fsf = port.moffat_fsf_image((23, 23), 0.2, fwhm_arcsec=1.2, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    init = np.dstack([rs.rand(H, W) * 4, 2 + rs.rand(H, W) * 6, 0.7 + rs.rand(H, W) * 2])
+    _compare_chain(nat, data, fsf, lsf, var, None, init, 6, 1, seed=17, mode=mode)
