@@ -459,13 +459,44 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
     if (n_sets > 0) pb.n_chains = n_sets;        // explicit parameter sets (first n_sets chain slots)
     const size_t HW = (size_t)pb.H * pb.W;
     {
-        const int threads = 256, wpb = threads / 32;
+        const int threads = std::max(256, ((pb.Dp + 31) / 32) * 32);
+        const int spb = threads / pb.Dp;
         size_t total = (size_t)pb.n_chains * HW;
-        unsigned blocks = (unsigned)std::min<size_t>((total + wpb - 1) / wpb, 148 * 16);
-        size_t smem = ((size_t)pb.P + (size_t)wpb * pb.Dp) * sizeof(double);
+        unsigned blocks = (unsigned)std::min<size_t>((total + spb - 1) / spb, 148 * 32);
+        size_t smem = ((size_t)pb.P + (pb.P + 1) / 2 + (size_t)spb * pb.P + (size_t)spb * 4) * sizeof(double);
+        if (total >= ((size_t)1 << 31)) return fail(D3D_EINVAL, "too many spaxels for one forward call");
         lines_kernel<<<blocks, threads, smem, c->stream>>>(pb, d_params, c->d_lines, convolve);
         c->launches++;
         CK(cudaGetLastError());
+    }
+    // register-tiled kernel for the common FSF widths (Dp is even: z-pairs), else the scalar one
+    {
+        const int TYt = 8, TXt = 16, ZCt = 16;
+        size_t smem_t = ((size_t)((pb.fh * pb.fw + 1) & ~1) +
+                         (size_t)(TYt + pb.fh - 1) * (TXt + pb.fw - 1) * ZCt) * sizeof(double);
+        bool ok = smem_t <= 200 * 1024 && !getenv("D3D_STENCIL_SCALAR") && pb.Dp % 2 == 0;
+        dim3 grid_t((unsigned)(pb.n_chains * ((pb.H + TYt - 1) / TYt) * ((pb.W + TXt - 1) / TXt)),
+                    (unsigned)((pb.Dp + ZCt - 1) / ZCt));
+        bool launched = false;
+#define D3D_TILED(FWV)                                                                              \
+        if (ok && !launched && pb.fw == FWV) {                                                      \
+            if (c->dtype == D3D_F64) {                                                              \
+                CK(cudaFuncSetAttribute(stencil_tiled_kernel<double, FWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+                stencil_tiled_kernel<double, FWV><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev); \
+            } else {                                                                                \
+                CK(cudaFuncSetAttribute(stencil_tiled_kernel<float, FWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+                stencil_tiled_kernel<float, FWV><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev); \
+            }                                                                                       \
+            launched = true;                                                                        \
+        }
+        D3D_TILED(3) D3D_TILED(5) D3D_TILED(7) D3D_TILED(9) D3D_TILED(11) D3D_TILED(13)
+        D3D_TILED(15) D3D_TILED(17) D3D_TILED(21)
+#undef D3D_TILED
+        if (launched) {
+            c->launches++;
+            CK(cudaGetLastError());
+            return 0;
+        }
     }
     int TY, TX, ZC; size_t smem;
     int rc = stencil_config(c, &TY, &TX, &ZC, &smem);

@@ -143,6 +143,16 @@ __device__ __forceinline__ double conv_at(const double* g, const double* K, int 
 
 enum { R_B = 0, R_C, R_PO, R_QOO, R_QON, R_QNN, R_A, R_N };
 
+#ifdef D3D_TRACE
+// Debug build only: absolute clock64() stamps of named events for a few consecutive sites.
+__device__ unsigned long long g_trace[64 * 32];
+#define TR(ev)                                                                              \
+    do { if (lane == 0 && blockIdx.x == 0 && it == it0 + 3 && j >= 700 && j < 764)          \
+             g_trace[(j - 700) * 32 + (ev)] = clock64(); } while (0)
+#else
+#define TR(ev)
+#endif
+
 #ifdef D3D_PHASE_TIMING
 // Debug build only: per-phase clock64() accumulators (window warp 0 / scalar warps, lane 0).
 __device__ unsigned long long g_phase[32];
@@ -1021,36 +1031,61 @@ __global__ void eval_kernel(const __grid_constant__ Problem pb, int chain, int s
 // Pass 1 (spectral): lines[chain][y][x][Dp] = mask * a * (lsf (*) gaussian(c,w)); one warp
 // per spaxel, the Gaussian is exchanged through shared memory.
 __global__ void lines_kernel(const __grid_constant__ Problem pb, const double* params, double* lines, int convolve) {
+    // one thread per (spaxel, channel): per-spaxel constants by the channel-0 thread, Gaussian
+    // -> shared memory (zero-padded circular buffer of length P per spaxel) -> the taps of the
+    // circular LSF kernel -> lines[chain][y][x][z]
     extern __shared__ double smem_raw[];
-    double* K = smem_raw;                         // [P]
-    double* g = K + pb.P;                         // [warps][Dp]
-    const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < pb.P; i += blockDim.x) K[i] = pb.kcirc[i];
-    __syncthreads();
-    const size_t HW = (size_t)pb.H * pb.W;
-    const size_t total = (size_t)pb.n_chains * HW;
-    double* gw = g + (size_t)warp * pb.Dp;
-    for (size_t sp = (size_t)blockIdx.x * wpb + warp; sp < total; sp += (size_t)gridDim.x * wpb) {
-        const int chain = (int)(sp / HW);
-        const size_t site = sp - (size_t)chain * HW;
-        const int cube = chain / pb.chains_per_cube;
-        const bool on = pb.mask[(size_t)cube * HW + site] == 1;
-        const double* p = params + sp * 3;
-        const double a = p[0], c = p[1], w = p[2];
-        double* out = lines + sp * pb.Dp;
-        if (!on) {
-            for (int z = lane; z < pb.Dp; z += 32) out[z] = 0.0;
-            continue;
+    double* Kv = smem_raw;                        // [P] tap values
+    int* Km = (int*)(Kv + pb.P);                  // [P] tap offsets
+    double* g = Kv + pb.P + (pb.P + 1) / 2;       // [spb][P]
+    const int D = pb.D, Dp = pb.Dp, P = pb.P, nt = pb.ntaps;
+    const int spb = blockDim.x / Dp;              // spaxels per block and pass
+    double* par = g + (size_t)spb * P;            // [spb][4]: a, c, 1/(2w^2), on
+    const int ls = threadIdx.x / Dp, z = threadIdx.x - ls * Dp;
+    const bool mine = ls < spb;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) { Kv[i] = pb.ktap_v[i]; Km[i] = pb.ktap_m[i]; }
+    for (int i = threadIdx.x; i < spb * P; i += blockDim.x) g[i] = 0.0;
+    const unsigned HW = (unsigned)(pb.H * pb.W);
+    const unsigned total = (unsigned)pb.n_chains * HW;      // (host guarantees < 2^31)
+    double* gw = g + (size_t)ls * P;
+    for (unsigned base = blockIdx.x * spb; base < total; base += gridDim.x * spb) {
+        const unsigned sp = base + ls;
+        const bool live = mine && sp < total;
+        __syncthreads();
+        if (live && z == 0) {
+            const unsigned chain = sp / HW, site = sp - chain * HW;
+            const bool on = pb.mask[(size_t)(chain / pb.chains_per_cube) * HW + site] == 1;
+            const double* p = params + (size_t)sp * 3;
+            const double w = p[2];
+            par[ls * 4 + 0] = p[0]; par[ls * 4 + 1] = p[1];
+            par[ls * 4 + 2] = 1.0 / (2.0 * (w * w));
+            par[ls * 4 + 3] = on ? 1.0 : 0.0;
         }
-        for (int z = lane; z < pb.Dp; z += 32)
-            gw[z] = z < pb.D ? a * unit_gaussian(z, c, w) : 0.0;     // lib/line_models.py:109
-        __syncwarp();
-        for (int z = lane; z < pb.Dp; z += 32) {
+        __syncthreads();
+        const bool on = live && par[ls * 4 + 3] != 0.0;
+        if (on && z < D) {
+            const double d = (double)z - par[ls * 4 + 1];
+            gw[z] = par[ls * 4 + 0] * exp(-1.0 * (d * d) * par[ls * 4 + 2]);   // lib/line_models.py:109
+        }
+        __syncthreads();
+        if (live) {
             double v = 0.0;
-            if (z < pb.D) v = (convolve && pb.has_lsf) ? conv_at(gw, K, z, pb.D, pb.P) : gw[z];
-            out[z] = v;
+            if (on && z < D) {
+                if (convolve && pb.has_lsf) {
+                    double a0 = 0.0, a1 = 0.0;
+                    int t = 0;
+                    for (; t + 1 < nt; t += 2) {
+                        a0 = fma(Kv[t], gw[(z - Km[t]) & (P - 1)], a0);
+                        a1 = fma(Kv[t + 1], gw[(z - Km[t + 1]) & (P - 1)], a1);
+                    }
+                    if (t < nt) a0 = fma(Kv[t], gw[(z - Km[t]) & (P - 1)], a0);
+                    v = a0 + a1;
+                } else {
+                    v = gw[z];
+                }
+            }
+            lines[(size_t)sp * Dp + z] = v;
         }
-        __syncwarp();
     }
 }
 
@@ -1257,3 +1292,4 @@ __global__ void conv1d_kernel(const double* lines, const double* kcirc, double* 
 }  // namespace d3d
 
 #include "d3d_slide.cuh"
+#include "d3d_stencil.cuh"

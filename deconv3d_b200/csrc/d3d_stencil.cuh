@@ -1,0 +1,114 @@
+// d3d_stencil.cuh -- register-tiled spatial pass of the forward model.
+//
+// sim[z][y'][x'] = sum_{j,k} F[j][k] * lines[z][y'+fhh-j][x'+fhw-k]   (true 2-D convolution,
+// zero 'same' borders: scipy.signal.convolve2d(...,'same') at lib/run.py:1027-1029, equal to
+// the paste of lib/run.py:697-706), fused with residual = data - sim and 0.5*sum(e^2/var).
+//
+// CTA = 256 threads = 8 z-pairs x 4 x-blocks x 8 rows; a thread produces RX = 4 consecutive
+// x outputs for one z-pair (8 accumulators).  The (TY+fh-1) x (TX+FW-1) x 16-channel halo tile
+// of `lines` sits in shared memory z-fastest: the 8 z-pair lanes of an element read 128
+// contiguous bytes (one conflict-free LDS.128 wavefront per quarter warp).  Per FSF row a
+// thread loads FW+3 tile vectors once and re-uses each of them for up to 4 outputs, and every
+// F[j][k] (one broadcast LDS) for 8 FMAs: ~3.6 DFMA per shared-memory load instead of 0.5
+// in the scalar kernel, which is what moves the pass from LDS-bound to the FP64 pipe.
+#pragma once
+
+namespace d3d {
+
+template <typename T> struct Pair;
+template <> struct Pair<double> { typedef double2 P; };
+template <> struct Pair<float>  { typedef float2  P; };
+
+template <typename T, int FW>
+__global__ void __launch_bounds__(256, 2)
+stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restrict__ lines,
+                     double* sim_out, int write_err, double* chi2_out) {
+    const int TY = 8, TX = 16, RX = 4, ZC = 16;
+    extern __shared__ double smem_raw[];
+    const int fh = pb.fh, Dp = pb.Dp, D = pb.D, H = pb.H, W = pb.W;
+    const int hx = TX + FW - 1, hy = TY + fh - 1;
+    double* F = smem_raw;                                   // [fh][FW]
+    double* tile = F + ((fh * FW + 1) & ~1);                // [hy][hx][ZC], 16-byte aligned
+    const int ty_n = (H + TY - 1) / TY, tx_n = (W + TX - 1) / TX;
+    const int chain = blockIdx.x / (ty_n * tx_n);
+    const int trem = blockIdx.x - chain * ty_n * tx_n;
+    const int ty0 = (trem / tx_n) * TY, tx0 = (trem % tx_n) * TX;
+    const int z0 = blockIdx.y * ZC;
+    const int cube = chain / pb.chains_per_cube;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < fh * FW; i += 256) F[i] = pb.fsf[i];
+    const double* lc = lines + (size_t)chain * H * W * Dp;
+    for (int i = tid; i < hy * hx * (ZC / 2); i += 256) {    // double2 granularity
+        const int zq = i & 7, s = i >> 3;
+        const int sy = s / hx, sx = s - sy * hx;
+        const int gy = ty0 + sy - pb.fhh, gx = tx0 + sx - pb.fhw;
+        const int z = z0 + 2 * zq;
+        double2 v = make_double2(0.0, 0.0);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W && z < Dp)
+            v = *(const double2*)(lc + ((size_t)gy * W + gx) * Dp + z);
+        *(double2*)(tile + (size_t)s * ZC + 2 * zq) = v;
+    }
+    __syncthreads();
+
+    const int zq = tid & 7, xb = (tid >> 3) & 3, oy = tid >> 5;
+    double acc[RX][2];
+#pragma unroll
+    for (int r = 0; r < RX; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
+    for (int j = 0; j < fh; ++j) {
+        // tile row of (y' + fhh - j): oy + fh - 1 - j; element u of the window = sx xb*4 + u
+        const double* trow = tile + ((size_t)(oy + fh - 1 - j) * hx + xb * RX) * ZC + 2 * zq;
+        const double* frow = F + j * FW;
+        double2 v[FW + RX - 1];
+#pragma unroll
+        for (int u = 0; u < FW + RX - 1; ++u) v[u] = *(const double2*)(trow + (size_t)u * ZC);
+#pragma unroll
+        for (int k = 0; k < FW; ++k) {
+            const double f = frow[k];
+#pragma unroll
+            for (int r = 0; r < RX; ++r) {                   // output r, tap k -> u = r + FW-1-k
+                acc[r][0] = fma(f, v[r + FW - 1 - k].x, acc[r][0]);
+                acc[r][1] = fma(f, v[r + FW - 1 - k].y, acc[r][1]);
+            }
+        }
+    }
+
+    const int gy = ty0 + oy;
+    const int z = z0 + 2 * zq;
+    double chi = 0.0;
+    if (gy < H && z < Dp) {
+        const T* data = (const T*)pb.data + (size_t)cube * H * W * Dp;
+        const T* ivc = pb.var_is_cube ? (const T*)pb.iv + (size_t)cube * H * W * Dp : nullptr;
+        const double ivs = pb.var_is_cube ? 0.0 : pb.iv_scalar[cube];
+        T* err = (T*)pb.err + (size_t)chain * H * W * Dp;
+        typedef typename Pair<T>::P P2;
+#pragma unroll
+        for (int r = 0; r < RX; ++r) {
+            const int gx = tx0 + xb * RX + r;
+            if (gx >= W) continue;
+            const size_t off = ((size_t)gy * W + gx) * Dp + z;
+            if (sim_out) {
+                if (z < D) sim_out[(size_t)chain * D * H * W + ((size_t)z * H + gy) * W + gx] = acc[r][0];
+                if (z + 1 < D) sim_out[(size_t)chain * D * H * W + ((size_t)(z + 1) * H + gy) * W + gx] = acc[r][1];
+            }
+            if (write_err || chi2_out) {
+                const P2 d = *(const P2*)(data + off);
+                double e0 = z < D ? (double)d.x - acc[r][0] : 0.0;
+                double e1 = z + 1 < D ? (double)d.y - acc[r][1] : 0.0;
+                if (write_err) { P2 o; o.x = (T)e0; o.y = (T)e1; *(P2*)(err + off) = o; }
+                if (chi2_out) {
+                    double w0 = ivs, w1 = ivs;
+                    if (ivc) { const P2 w = *(const P2*)(ivc + off); w0 = (double)w.x; w1 = (double)w.y; }
+                    chi = fma(e0 * e0, w0, chi);
+                    chi = fma(e1 * e1, w1, chi);
+                }
+            }
+        }
+    }
+    if (chi2_out) {
+        chi = warp_sum(chi);
+        if ((tid & 31) == 0) atomicAdd(chi2_out + chain, 0.5 * chi);
+    }
+}
+
+}  // namespace d3d
