@@ -183,7 +183,7 @@ static void choose_launch(d3d_ctx* c) {
         if (const char* e = getenv("D3D_ROW_VARIANT")) c->use_nc = c->ne != 0 && atoi(e) == 0;
         const int nwt_slide = (pb.fw + 1) * zl;
         c->slide_threads = ((nwt_slide + 31) / 32) * 32 + 96;
-        c->slide_smem = c->sweep_smem_base(pb);
+        c->slide_smem = c->sweep_smem_base(pb) + 2 * 4002 * sizeof(double) + 8964 * sizeof(unsigned short);
         c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384;
         if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
     }

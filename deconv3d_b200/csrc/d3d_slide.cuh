@@ -144,6 +144,18 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
     T* const errT = (T*)err;
     const T* const ivT = (const T*)ivc;
 
+    // truncated-normal tables (lib/rtnorm.py:227-2681) in shared memory for the inline table
+    // branch of warp B: x[4002], yu[4001] as doubles, ncell[8961] as 16-bit
+    double* const tx = smem_raw + smem_doubles(fh, fw, pb.P, Dp);
+    double* const tyu = tx + 4002;
+    unsigned short* const tnc = (unsigned short*)(tyu + 4002);
+    if (item == 0) {
+        for (int q = threadIdx.x; q < 4002; q += blockDim.x) tx[q] = pb.rt.x[q];
+        for (int q = threadIdx.x; q < 4001; q += blockDim.x) tyu[q] = pb.rt.yu[q];
+        for (int q = threadIdx.x; q < 8961; q += blockDim.x) tnc[q] = (unsigned short)pb.rt.ncell[q];
+        __syncthreads();
+    }
+
     double rate = pb.rate[chain];
     long long accepted = pb.accepted[chain];       // owned by lane 0 of warp B
     long long it = it0;
@@ -352,6 +364,22 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     // first z = log(1 - u) and e = -log(u') were evaluated ahead
                     const double z = spec_s[SP_Z1];
                     if (2.0 * as * as * spec_s[SP_E1] > z * z) { rs = as - z / as; done = true; }
+                }
+                else if (plain && as >= -2.00443204036 && as <= 3.48672170399) {     // :133-222
+                    // Chopin's table method, first try from the pre-drawn uniforms u4 (strip)
+                    // and u5 (position); tables in shared memory
+                    const int N = 4000;
+                    const int ka = tnc[3271 + (int)floor(as * 1631.73284006)];
+                    const int kb = bs >= 3.48672170399 ? N : tnc[3271 + (int)floor(bs * 1631.73284006)];
+                    if (kb - ka >= 5) {
+                        const int k = ka + (int)floor(spec_s[SP_U4] * (double)(kb + 1 - ka));
+                        if (k != N && !(k <= ka + 2 || (k >= kb && bs < 3.48672170399))) {
+                            const double u = spec_s[SP_U5];
+                            const double yuk = tyu[k], xk = tx[k], dk = tx[k + 1] - xk;
+                            const double ylk = k == 1 ? 0.053513975472 : (k <= 1954 ? tyu[k - 1] : tyu[k + 1]);
+                            if (yuk * u < ylk) { rs = xk + u * dk * yuk / ylk; done = true; }
+                        }
+                    }
                 }
                 if (!done) {                                     // every other branch / retry
                     Philox rng;

@@ -501,3 +501,30 @@ def test_large_fsf_generic_kernels_vs_oracle(nat, mode):
     var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
     init = np.dstack([rs.rand(H, W) * 4, 2 + rs.rand(H, W) * 6, 0.7 + rs.rand(H, W) * 2])
     _compare_chain(nat, data, fsf, lsf, var, None, init, 6, 1, seed=17, mode=mode)
+
+
+def test_mat_fixture_chain_vs_oracle(nat):
+    """The reference's own .mat fixture (tests/input/data14forAntoine.mat: 21x30x24 cube with
+    its per-voxel variance and 15x15 FSF, delta LSF as in tests/read_mat.py:93-94), started
+    from its ground-truth parameters: odd depth (padded channels), 15-row FSF (row-mapped
+    kernel with 21 register rows), non-square field."""
+    port, _, _ = _oracle()
+    g = load_golden('mat_kat')
+    data, var, fsf, params = g['data'], g['variance'], g['fsf'], g['params']
+    delta = port.gaussian_lsf_vector(0.0, 1.25e-4, data.shape[0])
+    mask = (port.above_percentile(data, 60) == 1).astype(float)        # tests/read_mat.py mask
+    _compare_chain(nat, data, fsf, delta, var, mask, params, 4, 1, seed=31)
+
+
+def test_tiny_field_smaller_than_fsf(nat):
+    """Field smaller than the FSF (H, W < fh, fw): every window is clipped on both sides."""
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(4)
+    D, H, W = 12, 5, 6
+    data = synthetic(D, H, W, 2)
+    fsf = port.gaussian_fsf_image(1.0, 0.2)                            # 13x13
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    init = np.dstack([rs.rand(H, W) * 4, 2 + rs.rand(H, W) * 6, 0.7 + rs.rand(H, W) * 2])
+    var = np.array([0.05 ** 2])      # (the default variance guess needs H > 6, lib/run.py:187)
+    _compare_chain(nat, data, fsf, lsf, var, None, init, 6, 1, seed=8)
+    _compare_chain(nat, data, fsf, lsf, var, None, init, 5, 1, seed=9, mode='colour')
