@@ -24,7 +24,10 @@ SYMBOLS = [
     'd3d_set_rng', 'd3d_set_params', 'd3d_get_params', 'd3d_init_params_uniform',
     'd3d_forward', 'd3d_simulate', 'd3d_simulate_clean', 'd3d_get_residual', 'd3d_conv1d',
     'd3d_rtnorm', 'd3d_delta_logl', 'd3d_sweep', 'd3d_get_counters',
+    'd3d_set_tile', 'd3d_tile_record_slots', 'd3d_colour_begin', 'd3d_colour_phase',
+    'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control',
 ]
+RECORD_DOUBLES = 8
 
 
 class NativeError(RuntimeError):
@@ -86,12 +89,19 @@ def load():
     lib.d3d_delta_logl.argtypes = [vp, ci, ci, ci, vp, vp]
     lib.d3d_sweep.argtypes = [vp, i64, i64, ci, ci, ci, cd, vp, vp, i64, vp, vp, vp]
     lib.d3d_get_counters.argtypes = [vp, vp, vp, vp]
+    lib.d3d_set_tile.argtypes = [vp, ci, ci, ci, ci]
+    lib.d3d_tile_record_slots.argtypes = [vp, vp]
+    lib.d3d_colour_begin.argtypes = [vp, i64, cd]
+    lib.d3d_colour_phase.argtypes = [vp, i64, ci, ci, vp]
+    lib.d3d_apply_records.argtypes = [vp, vp, i64]
+    lib.d3d_get_likelihoods.argtypes = [vp, vp]
+    lib.d3d_get_chain_control.argtypes = [vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('d3d_last_error',):
             fn.restype = ci
-    if lib.d3d_abi_version() != 1:
-        raise NativeError(EINVAL, 'libdeconv3d_b200.so has ABI %d, expected 1' % lib.d3d_abi_version())
+    if lib.d3d_abi_version() != 2:
+        raise NativeError(EINVAL, 'libdeconv3d_b200.so has ABI %d, expected 2' % lib.d3d_abi_version())
     _lib = lib
     return lib
 
@@ -269,6 +279,45 @@ class Context(object):
                                   float(min_acceptance_rate), _ptr(chain_out), _ptr(lik_out),
                                   int(n_rows), _ptr(acc), _ptr(its), ctypes.byref(ms)))
         return acc, its, ms.value
+
+    # ---- one cube tiled over several contexts (include/deconv3d_b200.h, "tiled") ----
+    def set_tile(self, y0, y1, x0, x1):
+        _check(self.lib.d3d_set_tile(self.h, int(y0), int(y1), int(x0), int(x1)))
+
+    def record_slots(self):
+        n = ctypes.c_int64(0)
+        _check(self.lib.d3d_tile_record_slots(self.h, ctypes.byref(n)))
+        return n.value
+
+    def colour_begin(self, iteration, min_acceptance_rate=0.0):
+        _check(self.lib.d3d_colour_begin(self.h, int(iteration), float(min_acceptance_rate)))
+
+    def colour_phase(self, iteration, cy, cx, records=None):
+        """records: None, a float64 numpy array [slots, 8] (filled synchronously) or an int
+        device address (e.g. ``tensor.data_ptr()``; filled asynchronously on the stream)."""
+        ptr = ctypes.c_void_p(records) if isinstance(records, int) else _ptr(records)
+        _check(self.lib.d3d_colour_phase(self.h, int(iteration), int(cy), int(cx), ptr))
+
+    def apply_records(self, records, n_records=None):
+        if isinstance(records, int):
+            ptr, n = ctypes.c_void_p(records), int(n_records)
+        else:
+            records = _f64(records).reshape(-1, RECORD_DOUBLES)
+            ptr, n = _ptr(records), records.shape[0]
+        _check(self.lib.d3d_apply_records(self.h, ptr, n))
+
+    def get_likelihoods(self):
+        D, H, W = self.shape
+        out = np.empty((self.n_chains, H, W))
+        _check(self.lib.d3d_get_likelihoods(self.h, _ptr(out)))
+        return out
+
+    def chain_control(self):
+        acc = np.zeros(self.n_chains, dtype=np.int64)
+        its = np.zeros(self.n_chains, dtype=np.int64)
+        act = np.zeros(self.n_chains, dtype=np.int32)
+        _check(self.lib.d3d_get_chain_control(self.h, _ptr(acc), _ptr(its), _ptr(act)))
+        return acc, its, act
 
     def counters(self):
         a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)

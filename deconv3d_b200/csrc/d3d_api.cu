@@ -57,6 +57,8 @@ struct d3d_ctx {
     static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
     void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
     bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
+    bool colour_attr_set = false, apply_attr_set = false;
+    double* d_rec_stage = nullptr; size_t rec_stage_cap = 0;   // staging of host-side record buffers
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
     int64_t window_voxels_per_sweep = 0;   // sum over cubes of sum_sites wh*ww*D * chains_per_cube
@@ -115,6 +117,7 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_problem(c);
     if (c->d_sched) cudaFree(c->d_sched);
+    if (c->d_rec_stage) cudaFree(c->d_rec_stage);
     if (c->rt_x) cudaFree(c->rt_x);
     if (c->rt_yu) cudaFree(c->rt_yu);
     if (c->rt_nc) cudaFree(c->rt_nc);
@@ -188,6 +191,7 @@ static void choose_launch(d3d_ctx* c) {
         if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
+    c->colour_attr_set = false;
 }
 
 extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int D, int H, int W,
@@ -348,6 +352,9 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     CK(cudaMemset(d_status, 0, sizeof(int)));
     pb.params = d_params; pb.accepted = d_acc; pb.iters = d_it; pb.rate = d_rate;
     pb.active = d_active; pb.status = d_status;
+    pb.ty0 = 0; pb.ty1 = H; pb.tx0 = 0; pb.tx1 = W;
+    pb.ry0 = 0; pb.ry1 = H; pb.rx0 = 0; pb.rx1 = W;
+    pb.lik_cur = nullptr; pb.acc_cur = nullptr;              // allocated by d3d_set_tile
     if ((rc = dalloc(c, &c->d_lines, (size_t)pb.n_chains * cube_elems * sizeof(double)))) return rc;
 
     choose_launch(c);
@@ -759,6 +766,7 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             std::vector<long long> prog(C, it0);
             if (c->sched_cap < flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long)) {
                 if (c->d_sched) cudaFree(c->d_sched);
+    if (c->d_rec_stage) cudaFree(c->d_rec_stage);
                 c->sched_cap = 2 * (flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long));
                 if (cudaMalloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; return cudaErrorMemoryAllocation; }
             }
@@ -800,30 +808,42 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
 }
 
 template <typename T, bool IV, int NE>
+static cudaError_t launch_colour_class(d3d_ctx* c, long long it, int cy, int cx, double* chain_dev,
+                                       double* lik_dev, long long rows_local, long long row_local) {
+    const Problem& pb = c->pb;
+    const int ne = NE ? NE : 7;
+    if (!c->colour_attr_set) {
+        if (NE == 0)
+            cudaFuncSetAttribute(sweep_colour_generic_kernel<T, IV>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        else
+            cudaFuncSetAttribute(sweep_colour_kernel<T, IV, ne>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        c->colour_attr_set = true;
+    }
+    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
+    dim3 grid(nly * nlx, pb.n_chains);
+    if (NE == 0)
+        sweep_colour_generic_kernel<T, IV><<<grid, c->generic_threads, c->sweep_smem, c->stream>>>(
+            pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
+    else
+        sweep_colour_kernel<T, IV, ne><<<grid, c->threads, c->sweep_smem, c->stream>>>(
+            pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+template <typename T, bool IV, int NE>
 static cudaError_t launch_colour(d3d_ctx* c, long long it, double* chain_dev, double* lik_dev,
                                  long long rows_local, long long row_local) {
     const Problem& pb = c->pb;
-    const int ne = NE ? NE : 7;
-    if (NE == 0)
-        cudaFuncSetAttribute(sweep_colour_generic_kernel<T, IV>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
-    else
-        cudaFuncSetAttribute(sweep_colour_kernel<T, IV, ne>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
-    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
-    dim3 grid(nly * nlx, pb.n_chains);
-    for (int cy = 0; cy < pb.fh; ++cy)
-        for (int cx = 0; cx < pb.fw; ++cx) {
+    cudaError_t e = cudaSuccess;
+    for (int cy = 0; cy < pb.fh && e == cudaSuccess; ++cy)
+        for (int cx = 0; cx < pb.fw && e == cudaSuccess; ++cx) {
             if (cy >= pb.H || cx >= pb.W) continue;
-            if (NE == 0)
-                sweep_colour_generic_kernel<T, IV><<<grid, c->generic_threads, c->sweep_smem, c->stream>>>(
-                    pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
-            else
-                sweep_colour_kernel<T, IV, ne><<<grid, c->threads, c->sweep_smem, c->stream>>>(
-                    pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
-            c->launches++;
+            e = launch_colour_class<T, IV, NE>(c, it, cy, cx, chain_dev, lik_dev, rows_local, row_local);
         }
-    return cudaGetLastError();
+    return e;
 }
 
 #define DISPATCH_NE(FN, T, IV, ...)                                         \
@@ -958,6 +978,148 @@ extern "C" int d3d_debug_phases(unsigned long long* out16, int reset) {
     return 0;
 }
 #endif
+
+// ------------------------------------------------------------------------------
+// Spatially tiled coloured sweep of ONE cube over several contexts
+// ------------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int rec_stage(d3d_ctx* c, size_t bytes) {
+    if (bytes <= c->rec_stage_cap) return 0;
+    if (c->d_rec_stage) cudaFree(c->d_rec_stage);
+    c->d_rec_stage = nullptr; c->rec_stage_cap = 0;
+    if (cudaMalloc(&c->d_rec_stage, bytes) != cudaSuccess)
+        return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) for the record staging buffer failed", bytes);
+    c->rec_stage_cap = bytes;
+    return 0;
+}
+
+extern "C" int d3d_set_tile(d3d_ctx* c, int y0, int y1, int x0, int x1) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_set_tile before d3d_set_problem");
+    Problem& pb = c->pb;
+    if (y0 < 0 || x0 < 0 || y1 > pb.H || x1 > pb.W || y0 > y1 || x0 > x1)
+        return fail(D3D_EINVAL, "d3d_set_tile: tile [%d,%d)x[%d,%d) outside the %dx%d field", y0, y1, x0, x1, pb.H, pb.W);
+    CK(cudaSetDevice(c->device));
+    if (!pb.lik_cur) {
+        const size_t n = (size_t)pb.n_chains * pb.H * pb.W;
+        int rc;
+        if ((rc = dalloc(c, &pb.lik_cur, n * sizeof(double)))) return rc;
+        if ((rc = dalloc(c, &pb.acc_cur, n))) return rc;
+        CK(cudaMemsetAsync(pb.lik_cur, 0, n * sizeof(double), c->stream));
+        CK(cudaMemsetAsync(pb.acc_cur, 0, n, c->stream));
+    }
+    pb.ty0 = y0; pb.ty1 = y1; pb.tx0 = x0; pb.tx1 = x1;
+    pb.ry0 = std::max(y0 - pb.fhh, 0); pb.ry1 = std::min(y1 + pb.fhh, pb.H);
+    pb.rx0 = std::max(x0 - pb.fhw, 0); pb.rx1 = std::min(x1 + pb.fhw, pb.W);
+    return 0;
+}
+
+extern "C" int d3d_tile_record_slots(d3d_ctx* c, int64_t* n_records) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_tile_record_slots before d3d_set_problem");
+    const Problem& pb = c->pb;
+    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
+    if (n_records) *n_records = (int64_t)pb.n_chains * nly * nlx;
+    return 0;
+}
+
+extern "C" int d3d_colour_begin(d3d_ctx* c, int64_t iteration, double min_acceptance_rate) {
+    if (!c || !c->have_problem || !c->have_params) return fail(D3D_ESTATE, "d3d_colour_begin needs a problem and parameters");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    sweep_begin_kernel<<<(pb.n_chains + 127) / 128, 128, 0, c->stream>>>(pb, iteration, min_acceptance_rate);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int d3d_colour_phase(d3d_ctx* c, int64_t iteration, int cy, int cx, double* records_out) {
+    if (!c || !c->have_problem || !c->have_params)
+        return fail(D3D_ESTATE, "d3d_colour_phase needs d3d_set_problem and parameters (+ d3d_forward)");
+    if (!c->have_tables) return fail(D3D_ESTATE, "d3d_colour_phase needs d3d_set_rtnorm_tables");
+    const Problem& pb = c->pb;
+    if (!pb.lik_cur) return fail(D3D_ESTATE, "d3d_colour_phase needs d3d_set_tile");
+    if (cy < 0 || cx < 0 || cy >= pb.fh || cx >= pb.fw) return fail(D3D_EINVAL, "colour class (%d,%d) outside the %dx%d FSF lattice", cy, cx, pb.fh, pb.fw);
+    if (iteration < 1 || iteration > 0xffffffffLL) return fail(D3D_EINVAL, "bad iteration");
+    CK(cudaSetDevice(c->device));
+    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
+    const int n = pb.n_chains * nly * nlx;
+    if (cy < pb.H && cx < pb.W) {
+        cudaError_t e = DISPATCH(launch_colour_class, c, (long long)iteration, cy, cx, nullptr, pb.lik_cur, 1LL, 0LL);
+        if (e != cudaSuccess) return fail(D3D_ECUDA, "colour phase launch failed: %s", cudaGetErrorString(e));
+    }
+    if (records_out) {
+        double* dst = records_out;
+        const bool dev = is_device_ptr(records_out);
+        if (!dev) { int rc = rec_stage(c, (size_t)n * REC_N * sizeof(double)); if (rc) return rc; dst = c->d_rec_stage; }
+        pack_records_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(pb, cy, cx, nly, nlx, dst);
+        c->launches++;
+        CK(cudaGetLastError());
+        if (!dev) {
+            CK(cudaMemcpyAsync(records_out, dst, (size_t)n * REC_N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    }
+    return 0;
+}
+
+extern "C" int d3d_apply_records(d3d_ctx* c, const double* records, int64_t n_records) {
+    if (!c || !c->have_problem || !c->have_params) return fail(D3D_ESTATE, "d3d_apply_records needs a problem and parameters");
+    const Problem& pb = c->pb;
+    if (!pb.lik_cur) return fail(D3D_ESTATE, "d3d_apply_records needs d3d_set_tile");
+    if (n_records < 0 || (n_records && !records)) return fail(D3D_EINVAL, "d3d_apply_records: bad arguments");
+    if (n_records == 0) return 0;
+    if (n_records > 0x7fffffffLL) return fail(D3D_EINVAL, "too many records");
+    CK(cudaSetDevice(c->device));
+    const double* src = records;
+    if (!is_device_ptr(records)) {
+        int rc = rec_stage(c, (size_t)n_records * REC_N * sizeof(double)); if (rc) return rc;
+        CK(cudaMemcpyAsync(c->d_rec_stage, records, (size_t)n_records * REC_N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        src = c->d_rec_stage;
+    }
+    if (!c->apply_attr_set) {
+        cudaFuncSetAttribute(apply_records_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        cudaFuncSetAttribute(apply_records_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        c->apply_attr_set = true;
+    }
+    if (c->dtype == D3D_F64)
+        apply_records_kernel<double><<<(unsigned)n_records, 256, c->sweep_smem, c->stream>>>(pb, src, (int)n_records);
+    else
+        apply_records_kernel<float><<<(unsigned)n_records, 256, c->sweep_smem, c->stream>>>(pb, src, (int)n_records);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int d3d_get_likelihoods(d3d_ctx* c, double* lik_out) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_get_likelihoods before d3d_set_problem");
+    const Problem& pb = c->pb;
+    if (!pb.lik_cur) return fail(D3D_ESTATE, "d3d_get_likelihoods needs d3d_set_tile");
+    if (!lik_out) return fail(D3D_EINVAL, "lik_out is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(lik_out, pb.lik_cur, (size_t)pb.n_chains * pb.H * pb.W * sizeof(double), cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int d3d_get_chain_control(d3d_ctx* c, int64_t* accepted_out, int64_t* iterations_out, int32_t* active_out) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_get_chain_control before d3d_set_problem");
+    const Problem& pb = c->pb;
+    CK(cudaSetDevice(c->device));
+    if (accepted_out) CK(cudaMemcpyAsync(accepted_out, pb.accepted, pb.n_chains * sizeof(long long), cudaMemcpyDefault, c->stream));
+    if (iterations_out) CK(cudaMemcpyAsync(iterations_out, pb.iters, pb.n_chains * sizeof(long long), cudaMemcpyDefault, c->stream));
+    if (active_out) CK(cudaMemcpyAsync(active_out, pb.active, pb.n_chains * sizeof(int), cudaMemcpyDefault, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int h_status = 0;
+    CK(cudaMemcpy(&h_status, pb.status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_status)
+        return fail(D3D_ENUMERIC, "cannot convert float NaN to integer: a NaN reached the truncated-normal sampler "
+                                  "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");
+    return 0;
+}
 
 extern "C" int d3d_get_counters(d3d_ctx* c, int64_t* kernel_launches, int64_t* last_sweep_bytes,
                                 int64_t* last_sweep_site_updates) {

@@ -65,6 +65,13 @@ struct Problem {
     double* rate;              // [chain]  cur_acceptance_rate      (lib/run.py:356-359)
     int* active;               // [chain]
     int* status;               // [1] sticky numeric-failure flag
+    // Spatial tiling of ONE cube over several contexts/GPUs (coloured mode, d3d_tile.cuh):
+    // only sites inside the tile are updated by this context; the residual is kept valid
+    // inside the region = tile grown by the FSF half-size.
+    int ty0, ty1, tx0, tx1;    // owned sites: ty0 <= y < ty1, tx0 <= x < tx1
+    int ry0, ry1, rx0, rx1;    // residual voxels this context keeps up to date
+    double* lik_cur;           // [chain][H][W] delta-logL of the latest update (tile mode)
+    uint8_t* acc_cur;          // [chain][H][W] its accept flag
 };
 
 // One proposal evaluated without touching any state (d3d_delta_logl).
@@ -249,6 +256,13 @@ __device__ __noinline__ void warp_line_profile(const Problem& pb, const Smem& sm
         for (int z = lane; z < pb.Dp; z += 32) out[z] = g[z];
     }
     PH_SUB(2);
+}
+
+// Residual update coefficient of one channel: e += F * (a * L_old - r * L_end).  Written with
+// explicit roundings so that every kernel (and the applier of remote tile updates,
+// d3d_tile.cuh) produces the same bits.
+__device__ __forceinline__ double upd_coef(double a, double lo, double r, double le) {
+    return fma(a, lo, -__dmul_rn(r, le));
 }
 
 // Proposal of one site (lib/run.py:370-388, 570-579), evaluated redundantly by
@@ -618,7 +632,7 @@ struct RowSite {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 const double lo = Lu_o[zp * VEC + v];
-                coef[v] = a * lo - r * (acc ? Lu_n[zp * VEC + v] : lo);
+                coef[v] = upd_coef(a, lo, r, acc ? Lu_n[zp * VEC + v] : lo);
             }
             // laundered base pointers: keeps the compiler from holding the NE row addresses of
             // the load phase in registers across the barriers
@@ -803,7 +817,7 @@ __device__ __forceinline__ int site_update_generic(const Problem& pb, const Smem
     if (worker) {
         double coef[VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) coef[v] = a * lo_v[v] - r * (acc ? ln_v[v] : lo_v[v]);
+        for (int v = 0; v < VEC; ++v) coef[v] = upd_coef(a, lo_v[v], r, acc ? ln_v[v] : lo_v[v]);
         int dy = col / ww, dx = col - dy * ww;
         for (int q = col; q < npos; q += NC) {
             const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
@@ -981,6 +995,7 @@ __global__ void sweep_begin_kernel(const __grid_constant__ Problem pb, long long
     const int iy = blockIdx.x / nlx, ix = blockIdx.x - iy * nlx;                            \
     const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;                                     \
     if (y >= pb.H || x >= pb.W) return;                                                     \
+    if (y < pb.ty0 || y >= pb.ty1 || x < pb.tx0 || x >= pb.tx1) return;                     \
     if (!pb.active[chain]) return;                                                          \
     const int site = y * pb.W + x;                                                          \
     if (pb.mask[(size_t)cube * pb.H * pb.W + site] != 1) return;                            \
@@ -1001,7 +1016,10 @@ sweep_colour_kernel(const __grid_constant__ Problem pb, long long it, int cy, in
     RowSite<T, IVCUBE, NE, false> rs;
     rs.init(pb);
     int acc = rs.run(pb, sm, chain, cube, site, (unsigned)it, crow, lrow, ev);
-    if (rs.warpB && rs.lane == 0 && acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+    if (rs.warpB && rs.lane == 0) {
+        if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+        if (pb.acc_cur) pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+    }
 }
 
 template <typename T, bool IVCUBE>
@@ -1011,7 +1029,10 @@ __global__ void sweep_colour_generic_kernel(const __grid_constant__ Problem pb, 
     D3D_COLOUR_PROLOGUE()
     int acc = site_update_generic<T, IVCUBE, false>(pb, sm, chain, cube, site, (unsigned)it, crow,
                                                     lrow, ev);
-    if (threadIdx.x == 0 && acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+    if (threadIdx.x == 0) {
+        if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+        if (pb.acc_cur) pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+    }
 }
 
 template <typename T, bool IVCUBE>
@@ -1293,3 +1314,4 @@ __global__ void conv1d_kernel(const double* lines, const double* kcirc, double* 
 
 #include "d3d_slide.cuh"
 #include "d3d_stencil.cuh"
+#include "d3d_tile.cuh"

@@ -1,18 +1,27 @@
 """
 Multi-GPU partitioning of the hot path.
 
-Chains (and survey galaxies) are independent units: they are sharded across the
+Two cases.  (1) Chains (and survey galaxies) are independent units: they are sharded across the
 ranks of one node with NO collective inside the sweep; every rank owns a
 contiguous block of unit ids and draws from the streams (seed, unit id), so the
 union of the shards is bit-identical to a single-GPU run over all units.  The
 only communication is the final gather of the (small) per-unit summaries.
+
+(2) ONE oversized cube (cfg4) does not shard by unit: its field is cut into
+rectangular tiles, one per context/GPU, and the coloured sweep is driven phase
+by phase (``TiledSweeper``).  The colour lattice is global, so the sites of a
+phase have disjoint windows across tiles; after each phase the ranks all-gather
+the 64-byte OUTCOME records of their site updates -- the one real exchange step
+of the path -- and every context rebuilds the rank-1 residual change of the
+remote records inside the region it reads (include/deconv3d_b200.h, "tiled").
 
 ``torch.distributed`` is plumbing here: NCCL on the GPU box, gloo in the CPU
 tests.
 """
 import numpy as np
 
-__all__ = ['shard_range', 'shard_sizes', 'gather_units', 'run_chains_sharded']
+__all__ = ['shard_range', 'shard_sizes', 'gather_units', 'run_chains_sharded',
+           'tile_grid', 'tile_bounds', 'TiledSweeper']
 
 
 def shard_sizes(n_units, world):
@@ -77,3 +86,151 @@ def run_chains_sharded(make_run, n_chains, group=None):
         shp = [local.shape[1:]]
         dist.broadcast_object_list(shp, src=0, group=group)
     return gather_units(local, n_chains, group)
+
+
+# ---------------------------------------------------------------------------------------
+# (2) one cube, spatial tiles
+# ---------------------------------------------------------------------------------------
+RECORD_DOUBLES = 8          # include/deconv3d_b200.h D3D_RECORD_DOUBLES
+
+
+def tile_grid(H, W, n_tiles):
+    """(rows, cols) with rows * cols == n_tiles whose tiles are closest to square
+    (8 tiles of a square field -> 2 x 4)."""
+    best = None
+    for rows in range(1, int(n_tiles) + 1):
+        if n_tiles % rows:
+            continue
+        cols = n_tiles // rows
+        th, tw = H / float(rows), W / float(cols)
+        score = max(th, tw) / max(min(th, tw), 1e-9)
+        if best is None or score < best[0] - 1e-12:
+            best = (score, rows, cols)
+    return best[1], best[2]
+
+
+def tile_bounds(H, W, n_tiles, index):
+    """(y0, y1, x0, x1) of tile ``index`` (row-major over tile_grid); the tiles partition
+    the field, sizes differ by at most one row / column."""
+    rows, cols = tile_grid(H, W, n_tiles)
+    ty, tx = divmod(int(index), cols)
+    y0, ny = shard_range(H, rows, ty)
+    x0, nx = shard_range(W, cols, tx)
+    return y0, y0 + ny, x0, x0 + nx
+
+
+class TiledSweeper(object):
+    """Coloured MH-within-Gibbs sweeps (lib/run.py:344-537 in colour-class order) of ONE cube
+    whose sites are split into tiles: ``contexts`` are this process' contexts (normally one,
+    on its GPU; several in the single-GPU tests), all set up with the SAME problem, the same
+    parameters and the same RNG; with a process group the tiles of all ranks form the grid.
+
+    The result is independent of the tiling: the random numbers of a site update are
+    addressed by (seed, chain, sweep, site), not by who draws them.
+    """
+
+    def __init__(self, contexts, field_hw, fsf_hw, group=None, use_torch=True):
+        self.ctxs = list(contexts)
+        self.H, self.W = int(field_hw[0]), int(field_hw[1])
+        self.fh, self.fw = int(fsf_hw[0]), int(fsf_hw[1])
+        self.group = group
+        self.dist = None
+        self.world, self.rank = 1, 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist = dist
+                self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        except ImportError:
+            pass
+        self.nlocal = len(self.ctxs)
+        self.n_tiles = self.world * self.nlocal
+        self.tiles = []
+        for i, ctx in enumerate(self.ctxs):
+            b = tile_bounds(self.H, self.W, self.n_tiles, self.rank * self.nlocal + i)
+            ctx.set_tile(*b)
+            self.tiles.append(b)
+        self.slots = self.ctxs[0].record_slots()
+        self.device_records = bool(getattr(self.ctxs[0], 'device_records', True)) and use_torch
+        if self.device_records:
+            import torch
+            dev = torch.device('cuda', torch.cuda.current_device())
+            # phase kernels, NCCL and appliers all go to ONE explicit stream (the legacy default
+            # stream has no handle a library context could be bound to)
+            self.torch = torch
+            self.stream = torch.cuda.Stream(device=dev)
+            for ctx in self.ctxs:
+                ctx.set_stream(self.stream.cuda_stream)
+            self.local = torch.empty((self.nlocal * self.slots, RECORD_DOUBLES),
+                                     dtype=torch.float64, device=dev)
+            self.all = (torch.empty((self.world * self.nlocal * self.slots, RECORD_DOUBLES),
+                                    dtype=torch.float64, device=dev)
+                        if self.world > 1 else self.local)
+        else:
+            self.local = np.empty((self.nlocal * self.slots, RECORD_DOUBLES))
+            self.all = self.local
+        self.exchanges = 0
+
+    # -- one colour phase on every local tile, then the exchange, then the appliers --
+    def _phase(self, it, cy, cx):
+        nb = self.slots * RECORD_DOUBLES * 8
+        for i, ctx in enumerate(self.ctxs):
+            if self.device_records:
+                ctx.colour_phase(it, cy, cx, self.local.data_ptr() + i * nb)
+            else:
+                ctx.colour_phase(it, cy, cx, self.local[i * self.slots:(i + 1) * self.slots])
+        if self.n_tiles == 1:
+            return
+        allrec = self.local
+        if self.world > 1:
+            if self.device_records:
+                with self.torch.cuda.stream(self.stream):
+                    self.dist.all_gather_into_tensor(self.all, self.local, group=self.group)
+                allrec = self.all
+            else:
+                import torch
+                mine = torch.from_numpy(self.local)
+                parts = [torch.empty_like(mine) for _ in range(self.world)]
+                self.dist.all_gather(parts, mine, group=self.group)
+                allrec = np.concatenate([p.numpy() for p in parts], axis=0)
+            self.exchanges += 1
+        n = self.n_tiles * self.slots
+        for ctx in self.ctxs:
+            if self.device_records:
+                ctx.apply_records(allrec.data_ptr(), n)
+            else:
+                ctx.apply_records(allrec, n)
+
+    def sweep(self, first_iteration, n_iterations, keep_one_in=1, refresh_every=1000,
+              min_acceptance_rate=0.0, chain_out=None, lik_out=None):
+        """Iterations [first, first + n).  chain_out [n_chains, rows, H, W, 3] and lik_out
+        [n_chains, rows, H, W] (numpy, optional) get row it // keep_one_in when
+        it % keep_one_in == 0, complete on every rank.  Returns (accepted, iterations) per
+        chain, identical on every rank."""
+        lead = self.ctxs[0]
+        for it in range(int(first_iteration), int(first_iteration + n_iterations)):
+            for ctx in self.ctxs:
+                ctx.colour_begin(it, min_acceptance_rate)
+            for cy in range(min(self.fh, self.H)):
+                for cx in range(min(self.fw, self.W)):
+                    self._phase(it, cy, cx)
+            if it % keep_one_in == 0:
+                row = it // keep_one_in
+                if chain_out is not None:
+                    chain_out[:, row] = lead.get_params()
+                if lik_out is not None:
+                    lik_out[:, row] = lead.get_likelihoods()
+            if refresh_every and it % refresh_every == 0:         # lib/run.py:525-534
+                for ctx in self.ctxs:
+                    ctx.forward()
+            if min_acceptance_rate > 0.0:
+                if not lead.chain_control()[2].any():
+                    break
+        acc, its, _ = lead.chain_control()
+        return acc, its
+
+    def finish(self):
+        """Rebuilds the full residual of every context from the (complete) parameters: during
+        the sweeps each context only maintains the part of it that its tile reads."""
+        for ctx in self.ctxs:
+            ctx.forward()

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3D_ABI_VERSION 1
+#define D3D_ABI_VERSION 2
 
 /* storage dtype of the residual / data / inverse-variance cubes */
 #define D3D_F32 0
@@ -170,6 +170,44 @@ int d3d_sweep(d3d_ctx* ctx, int64_t first_iteration, int64_t n_iterations,
               double min_acceptance_rate,
               double* chain_out, double* lik_out, int64_t n_rows,
               int64_t* accepted_out, int64_t* iterations_out, float* elapsed_ms);
+
+/* ---- one oversized cube tiled over several contexts / GPUs ------------------
+ *   The reference has a single process walk every spaxel
+ * of the cube (lib/run.py:362-367); here each context owns the sites of one
+ * rectangular tile and the coloured sweep is driven phase by phase so that the
+ * contexts can exchange the OUTCOMES of their site updates between two phases
+ * (the colour lattice (y mod fh, x mod fw) is global, hence the sites of a
+ * phase have disjoint windows across tiles too).  Every context holds the
+ * whole cube; its residual stays valid inside its tile grown by the FSF
+ * half-size, the only part its own updates read.  The exchange (NCCL
+ * all-gather, peer copies ...) belongs to the caller: deconv3d_b200/dist.py.
+ *
+ * A record is D3D_RECORD_DOUBLES float64: site (y*W+x, or -1 = empty slot),
+ * chain, a, c, w (the parameters after the update, lib/run.py:448,499,516),
+ * delta-logL (:430-432), accepted (:438-440), pad.  One phase fills
+ * n_chains * ceil(H/fh) * ceil(W/fw) slots (d3d_tile_record_slots).          */
+#define D3D_RECORD_DOUBLES 8
+/* Sites owned by this context: y0 <= y < y1, x0 <= x < x1 (default: the whole
+ * field).  Also restricts mode D3D_COLOURED of d3d_sweep to those sites. */
+int d3d_set_tile(d3d_ctx* ctx, int y0, int y1, int x0, int x1);
+int d3d_tile_record_slots(d3d_ctx* ctx, int64_t* n_records);
+/* Loop condition and acceptance-rate bookkeeping of lib/run.py:344-359, once
+ * per iteration and before its first phase. */
+int d3d_colour_begin(d3d_ctx* ctx, int64_t iteration, double min_acceptance_rate);
+/* Updates the owned sites of colour class (cy, cx) for `iteration` and writes
+ * their records (host or device buffer of d3d_tile_record_slots records, or
+ * NULL).  Asynchronous on the context's stream when the buffer is on the device. */
+int d3d_colour_phase(d3d_ctx* ctx, int64_t iteration, int cy, int cx, double* records_out);
+/* Applies the records of OTHER contexts (own and empty ones are skipped):
+ * parameters, delta-logL, accepted_count and the residual inside the region. */
+int d3d_apply_records(d3d_ctx* ctx, const double* records, int64_t n_records);
+/* Latest delta-logL of every site [n_chains][H][W] (the row lib/run.py:430-432
+ * would store); tile mode only. */
+int d3d_get_likelihoods(d3d_ctx* ctx, double* lik_out);
+/* accepted_count (:341,:440), cur_iteration and the running flag of every chain
+ * (any may be NULL); reports D3D_ENUMERIC like d3d_sweep. */
+int d3d_get_chain_control(d3d_ctx* ctx, int64_t* accepted_out, int64_t* iterations_out,
+                          int32_t* active_out);
 
 /* Introspection for benches: launches of library kernels so far, algorithmic
  * bytes of the last d3d_sweep (3*s*D*wh*ww per site update with a variance

@@ -23,7 +23,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert declared == set(_native.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), 'library does not export %s' % name
-    assert _native.load().d3d_abi_version() == 1
+    assert _native.load().d3d_abi_version() == 2
 
 
 def test_no_silent_cpu_fallback_without_gpu():
