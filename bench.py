@@ -56,6 +56,16 @@ def build_workload(name, chains):
                     chains_per_cube=1, var_kind='cube', sigma=0.05,
                     desc='survey batch: %d independent synthetic galaxies 32x32x32 per GPU, '
                          'FSF 11x11, per-galaxy data + variance' % chains)
+    if name == 'cfg4':
+        D, H, W = 64, chains, chains            # `chains` carries the field size here (1 chain)
+        # 41x41 Moffat stamp of FWHM 3 px, beta 2 (the cube keeps the 0.2"/px
+        # metadata of build_cube, so 3 px = 0.6")
+        inst = synthetic.muse_wfm_instrument('moffat', 41, fsf_fwhm=0.6, beta=2.0)
+        truth = synthetic.narrow_field_truth(D, H, W)
+        return dict(name=name, D=D, H=H, W=W, inst=inst, truth=truth[None], n_cubes=1,
+                    chains_per_cube=1, var_kind='cube', sigma=0.05,
+                    desc='one oversized synthetic cube %dx%dx64, Moffat FWHM 3 px beta 2 stamp 41x41, '
+                         'MUSE LSF (P = 64: full wrap), variance cube, 1 chain, spatial tiles' % (H, W))
     if name == 'cfg1':
         data = np.load(os.path.join(ROOT, 'tests', 'golden', 'muse_cube_01.npz'))['data'] * 1e20
         from deconv3d_b200 import MUSE
@@ -236,7 +246,8 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2x256', choices=['cfg2x256', 'cfg2', 'cfg1', 'cfg5'])
+    ap.add_argument('--workload', default='cfg2x256', choices=['cfg2x256', 'cfg2', 'cfg1', 'cfg5', 'cfg4'])
+    ap.add_argument('--field', type=int, default=256, help='cfg4: field side in spaxels')
     ap.add_argument('--mode', default='sequential', choices=['sequential', 'coloured'])
     ap.add_argument('--chains', type=int, default=None, help='chains (or galaxies) per GPU')
     ap.add_argument('--sweeps', type=int, default=None, help='Gibbs sweeps per step')
@@ -251,9 +262,11 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     chains = args.chains if args.chains is not None else \
-        {'cfg2x256': 256, 'cfg2': 1, 'cfg1': 1, 'cfg5': 512}[args.workload]
+        {'cfg2x256': 256, 'cfg2': 1, 'cfg1': 1, 'cfg5': 512, 'cfg4': 1}[args.workload]
     sweeps = args.sweeps if args.sweeps is not None else \
-        {'cfg2x256': 20, 'cfg2': 200, 'cfg1': 200, 'cfg5': 20}[args.workload]
+        {'cfg2x256': 20, 'cfg2': 200, 'cfg1': 200, 'cfg5': 20, 'cfg4': 1}[args.workload]
+    if args.workload == 'cfg4':
+        return bench_tiled(args, rank, local_rank, world, sweeps)
 
     if args.impl == 'reference':
         if rank != 0:
@@ -403,6 +416,109 @@ def main():
             'sample': '1 chain, %d timed sweeps (%d site updates) of the same cube on one host core '
                       '(numpy is single-threaded on this path); host has %d cores'
                       % (cs - 1, upd, os.cpu_count() or 1)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_tiled(args, rank, local_rank, world, sweeps):
+    """cfg4: ONE oversized cube, sites tiled over the ranks, coloured sweep with one exchange of
+    outcome records (NCCL all-gather) per colour phase.  Strong scaling: the cube is fixed."""
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: deconv3d_b200 has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from deconv3d_b200 import _native, rtnorm_tables
+    from deconv3d_b200 import dist as d3dist
+    wl = build_workload('cfg4', args.field)
+    arrays = realise(wl, 0)                       # the same cube on every rank
+    D, H, W = wl['D'], wl['H'], wl['W']
+    fh, fw = arrays['fsf'].shape
+    ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
+    ctx.set_rtnorm_tables(*rtnorm_tables.tables())
+    ctx.set_rng(42, 0)
+    t0 = time.perf_counter()
+    ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                    arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=1)
+    ctx.init_params_uniform()                     # Philox-addressed: identical on every rank
+    ctx.forward(write_err=True)
+    setup_s = time.perf_counter() - t0
+    sw = d3dist.TiledSweeper([ctx], (H, W), (fh, fw))
+    stream = sw.stream
+    it = 1
+    for _ in range(args.warmup):
+        sw.sweep(it, sweeps, refresh_every=0)
+        it += sweeps
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = ctx.counters()['kernel_launches']
+    step_ms = []
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sw.sweep(it, sweeps, refresh_every=0)
+            e1.record(stream)
+            e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            it += sweeps
+        barrier()
+    launches = ctx.counters()['kernel_launches'] - launches0
+    # end to end: one sweep with the chain row and the likelihoods read back to the host
+    chain = np.zeros((1, it + sweeps, H, W, 3))
+    lik = np.zeros((1, it + sweeps, H, W))
+    barrier()
+    t0 = time.perf_counter()
+    sw.sweep(it, sweeps, keep_one_in=1, refresh_every=0, chain_out=chain, lik_out=lik)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([float(np.sum(step_ms)), e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    n_sites = H * W
+    updates = float(n_sites) * sweeps * args.steps
+    value = updates / (total_ms * 1e-3)
+    s = 8 if args.dtype == 'f64' else 4
+    fhh, fhw = (fh - 1) // 2, (fw - 1) // 2
+    sum_wh = sum(min(y + fhh + 1, H) - max(y - fhh, 0) for y in range(H))
+    sum_ww = sum(min(x + fhw + 1, W) - max(x - fhw, 0) for x in range(W))
+    bytes_sweep = 3.0 * s * D * sum_wh * sum_ww
+    peak, peak_src = measured_peak()
+    achieved = bytes_sweep * sweeps * args.steps / (total_ms * 1e-3) / 1e9
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': wl['desc'], 'mode': 'coloured, tiles %dx%d' % d3dist.tile_grid(H, W, world),
+                   'sweeps_per_step': sweeps, 'sites_per_sweep': n_sites,
+                   'phases_per_sweep': min(fh, H) * min(fw, W),
+                   'exchange': 'all-gather of %d records x 64 B per rank and phase' % sw.slots,
+                   'l2': 'window traffic per sweep (%.0f GB) exceeds L2' % (bytes_sweep / 1e9)},
+        'sweeps_per_s': value / n_sites, 'gpu_launches': int(launches),
+        'clocks': clocks.summary(),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak * world, 'unit': 'GB/s',
+                     'frac': achieved / (peak * world), 'traffic': None, 'peak_source': peak_src,
+                     'kernel': 'sweep_colour_generic_kernel',
+                     'note': 'whole-step figure (phase kernels + exchange + appliers), all GPUs'},
+        'e2e': {'value': n_sites * sweeps / e2e_s, 'unit': UNIT,
+                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': int(n_sites * 4 * 8 * sweeps),
+                'ms_per_step': e2e_s * 1e3, 'setup_s': setup_s,
+                'api': 'TiledSweeper.sweep(..., chain_out, lik_out)'},
+    }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -21,6 +21,16 @@ def halpha_truth(D=40, H=40, W=40):
     return np.dstack([a, c, w])
 
 
+def narrow_field_truth(D=64, H=256, W=256):
+    """cfg4 truth maps (one oversized cube): the cfg2 galaxy stretched over the larger field."""
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    r2 = (yy - (H - 1) / 2.) ** 2 + (xx - (W - 1) / 2.) ** 2
+    a = 10.0 * np.exp(-r2 / (2. * (0.15 * H) ** 2))
+    c = D / 2. + 0.15 * D * np.tanh((xx - (W - 1) / 2.) / (0.2 * W))
+    w = np.full((H, W), 2.5)
+    return np.dstack([a, c, w])
+
+
 def muse_wfm_instrument(fsf='moffat', fsf_size=13, fsf_fwhm=0.8, beta=2.5):
     """MUSE WFM: 0.2"/px, 1.25 A/channel; Moffat FWHM 0.8" beta 2.5 truncated to an odd stamp
     (the reference's Moffat image is cube-sized, lib/spread_functions.py:167) or the default

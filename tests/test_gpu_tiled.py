@@ -134,3 +134,22 @@ def test_tile_api_errors(nat):
     assert (mask[ys, xs] == 1).all()
     p = ctx.get_params()[0]
     assert np.array_equal(rec[rec[:, 0] >= 0][:, 2:5], p[ys, xs])
+
+
+def test_tiled_nccl_multi_gpu(nat):
+    """One rank per GPU, records exchanged by NCCL (needs >= 2 GPUs; the single-GPU box of the
+    round-end run skips it)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs at least 2 GPUs')
+    n = 2 if n < 4 else 4
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+                          '--nproc-per-node', str(n), '--master-addr', '127.0.0.1',
+                          '--master-port', '29533', os.path.join(here, 'run_tiled_nccl.py')],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and 'TILED NCCL OK' in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
