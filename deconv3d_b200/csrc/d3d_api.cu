@@ -58,6 +58,9 @@ struct d3d_ctx {
     void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
     bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
     bool colour_attr_set = false, apply_attr_set = false;
+    bool cluster_attr_set = false, apply_cluster_attr_set = false;
+    int* d_sites_colour = nullptr;      // [cube][max_sites] colour-class order
+    int cluster = 0;                    // > 1: generic colour kernels work a site with a CTA cluster
     double* d_rec_stage = nullptr; size_t rec_stage_cap = 0;   // staging of host-side record buffers
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
@@ -192,6 +195,13 @@ static void choose_launch(d3d_ctx* c) {
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
     c->colour_attr_set = false;
+    c->apply_attr_set = false;
+    c->cluster_attr_set = false;
+    c->apply_cluster_attr_set = false;
+    // big windows: split one site over a thread-block cluster (d3d_tile.cuh)
+    c->cluster = (c->ne == 0 && (long long)pb.fh * pb.fw * pb.Dp >= 32768) ? 4 : 0;
+    if (const char* e = getenv("D3D_CLUSTER")) c->cluster = c->ne == 0 ? atoi(e) : 0;
+    if (c->cluster < 2) c->cluster = 0;
 }
 
 extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int D, int H, int W,
@@ -279,12 +289,25 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
                     wvox += (int64_t)wh * ww * D * chains_per_cube;
                 }
     }
+    // the same sites in colour-class order (classes (y mod fh, x mod fw) row-major, sites of a
+    // class row-major): coloured mode with many chains walks this list chain by chain
+    std::vector<int> csites((size_t)n_cubes * max_sites, 0);
+    for (int q = 0; q < n_cubes; ++q) {
+        int k = 0;
+        for (int cy = 0; cy < std::min(fh, H); ++cy)
+            for (int cx = 0; cx < std::min(fw, W); ++cx)
+                for (int y = cy; y < H; y += fh)
+                    for (int x = cx; x < W; x += fw)
+                        if (hmask[q * HW + (size_t)y * W + x] == 1) csites[(size_t)q * max_sites + k++] = y * W + x;
+    }
     c->window_voxels_per_sweep = wvox;
     c->h_nsites = nsites;
     pb.max_sites = max_sites;
     uint8_t* d_mask; int* d_sites; int* d_ns;
     if ((rc = dalloc(c, &d_mask, hmask.size()))) return rc;
     if ((rc = dalloc(c, &d_sites, sites.size() * sizeof(int)))) return rc;
+    if ((rc = dalloc(c, &c->d_sites_colour, csites.size() * sizeof(int)))) return rc;
+    CK(cudaMemcpy(c->d_sites_colour, csites.data(), csites.size() * sizeof(int), cudaMemcpyHostToDevice));
     if ((rc = dalloc(c, &d_ns, n_cubes * sizeof(int)))) return rc;
     CK(cudaMemcpy(d_mask, hmask.data(), hmask.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_sites, sites.data(), sites.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -766,7 +789,6 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             std::vector<long long> prog(C, it0);
             if (c->sched_cap < flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long)) {
                 if (c->d_sched) cudaFree(c->d_sched);
-    if (c->d_rec_stage) cudaFree(c->d_rec_stage);
                 c->sched_cap = 2 * (flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long));
                 if (cudaMalloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; return cudaErrorMemoryAllocation; }
             }
@@ -823,6 +845,25 @@ static cudaError_t launch_colour_class(d3d_ctx* c, long long it, int cy, int cx,
     }
     const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
     dim3 grid(nly * nlx, pb.n_chains);
+    if (NE == 0 && c->cluster) {
+        if (!c->cluster_attr_set) {
+            cudaFuncSetAttribute(sweep_colour_cluster_kernel<T, IV>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+            c->cluster_attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nly * nlx * c->cluster, pb.n_chains);
+        cfg.blockDim = dim3(320);
+        cfg.dynamicSmemBytes = c->sweep_smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        c->launches++;
+        return cudaLaunchKernelEx(&cfg, sweep_colour_cluster_kernel<T, IV>, pb, it, cy, cx, nlx, chain_dev,
+                                  lik_dev, rows_local, row_local);
+    }
     if (NE == 0)
         sweep_colour_generic_kernel<T, IV><<<grid, c->generic_threads, c->sweep_smem, c->stream>>>(
             pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);
@@ -896,6 +937,14 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         cudaMemsetAsync(lik_dev, 0, (size_t)pb.n_chains * rows_local * HW * sizeof(double), c->stream);
     }
 
+    bool colour_by_chain = false;
+    if (mode == D3D_COLOURED) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const bool whole = pb.ty0 == 0 && pb.tx0 == 0 && pb.ty1 == pb.H && pb.tx1 == pb.W;
+        colour_by_chain = whole && pb.n_chains >= (2 * sms) / 3;
+        if (const char* ev = getenv("D3D_COLOUR_BY_CHAIN")) colour_by_chain = whole && atoi(ev) != 0;
+    }
     cudaEventRecord(c->ev0, c->stream);
     cudaError_t e = cudaSuccess;
     long long it = it_begin;
@@ -909,6 +958,18 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         if (mode == D3D_SEQ_EXACT) {
             e = DISPATCH(launch_seq, c, it, seg_end, keep_one_in, min_acceptance_rate, chain_dev,
                          lik_dev, row_first, rows_local);
+        } else if (colour_by_chain) {
+            // many chains: one CTA per chain walks the sites in colour-class order -- the same
+            // result as one launch per class (the sites of a class do not interact), without
+            // the fh*fw launches and with every SM busy on its own chain
+            const int* row_major = c->pb.sites;
+            const bool slide = c->use_slide;
+            c->pb.sites = c->d_sites_colour;
+            c->use_slide = false;
+            e = DISPATCH(launch_seq, c, it, seg_end, keep_one_in, min_acceptance_rate, chain_dev,
+                         lik_dev, row_first, rows_local);
+            c->pb.sites = row_major;
+            c->use_slide = slide;
         } else {
             for (long long k = it; k < seg_end && e == cudaSuccess; ++k) {
                 sweep_begin_kernel<<<(pb.n_chains + 127) / 128, 128, 0, c->stream>>>(pb, k, min_acceptance_rate);
@@ -1084,6 +1145,26 @@ extern "C" int d3d_apply_records(d3d_ctx* c, const double* records, int64_t n_re
         cudaFuncSetAttribute(apply_records_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         cudaFuncSetAttribute(apply_records_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         c->apply_attr_set = true;
+    }
+    if (c->cluster) {
+        if (!c->apply_cluster_attr_set) {
+            cudaFuncSetAttribute(apply_records_cluster_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+            cudaFuncSetAttribute(apply_records_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+            c->apply_cluster_attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_records * c->cluster);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = c->sweep_smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        c->launches++;
+        if (c->dtype == D3D_F64) CK(cudaLaunchKernelEx(&cfg, apply_records_cluster_kernel<double>, pb, src, (int)n_records));
+        else CK(cudaLaunchKernelEx(&cfg, apply_records_cluster_kernel<float>, pb, src, (int)n_records));
+        return 0;
     }
     if (c->dtype == D3D_F64)
         apply_records_kernel<double><<<(unsigned)n_records, 256, c->sweep_smem, c->stream>>>(pb, src, (int)n_records);

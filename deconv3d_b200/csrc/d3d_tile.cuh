@@ -9,8 +9,10 @@
 // to the part of its residual it will read again (tile grown by the FSF half-size).  The
 // exchange itself (NCCL all-gather / peer copies) is the caller's: see deconv3d_b200/dist.py.
 #pragma once
+#include <cooperative_groups.h>
 
 namespace d3d {
+namespace cg = cooperative_groups;
 
 enum { REC_SITE = 0, REC_CHAIN, REC_A, REC_C, REC_W, REC_LIK, REC_ACC, REC_PAD, REC_N };
 
@@ -104,6 +106,285 @@ __global__ void apply_records_kernel(const __grid_constant__ Problem pb, const d
         }
     }
     if (tid == 0) {
+        prm[0] = a_n; prm[1] = c_n; prm[2] = w_n;
+        pb.lik_cur[(size_t)chain * HW + site] = r[REC_LIK];
+        const int acc = r[REC_ACC] != 0.0;
+        pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+        if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Large windows (generic FSF sizes, e.g. 41x41x64 = 860 KB per array at cfg4): ONE site is
+// worked by a thread-block CLUSTER.  Each CTA of the cluster takes a contiguous share of the
+// window positions, the six partial sums meet in the leader's shared memory (DSMEM), the leader
+// decides, every CTA reads the decision back through DSMEM and updates its share.  All CTAs
+// evaluate the proposal and both line profiles redundantly (deterministic, D values).
+// grid = (lattice slots * cluster size, chains), cluster = (CS, 1, 1).
+// ---------------------------------------------------------------------------
+template <typename T, bool IVCUBE>
+__global__ void __launch_bounds__(320)
+sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, int cy, int cx, int nlx,
+                            double* crow_base, double* lrow_base, long long rows_local,
+                            long long row_local) {
+    typedef typename Vec<T>::V V;
+    const int VEC = Vec<T>::N;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+    extern __shared__ double smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    const int chain = blockIdx.y;
+    const int cube = chain / pb.chains_per_cube;
+    const int slot = blockIdx.x / CS;
+    const int iy = slot / nlx, ix = slot - iy * nlx;
+    const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;
+    // (every exit below is taken by the whole cluster)
+    if (y >= pb.H || x >= pb.W) return;
+    if (y < pb.ty0 || y >= pb.ty1 || x < pb.tx0 || x >= pb.tx1) return;
+    if (!pb.active[chain]) return;
+    const int W = pb.W, H = pb.H, Dp = pb.Dp;
+    const int site = y * W + x;
+    const size_t HW = (size_t)H * W;
+    if (pb.mask[(size_t)cube * HW + site] != 1) return;
+    load_constants(sm, pb);
+    __syncthreads();
+    cluster.sync();                                    // every CTA of the cluster is running (DSMEM)
+    double* crow = crow_base ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3 : nullptr;
+    double* lrow = lrow_base ? lrow_base + ((size_t)chain * rows_local + row_local) * HW + site : nullptr;
+    EvalReq ev; ev.enabled = 0; ev.out = nullptr;
+
+    // 8 window warps + 2 scalar warps (proposal / new profile / decision, old profile): the
+    // window loads start at once instead of waiting behind the transcendental chains
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NWW = 8, nwarps = NWW;
+    Philox rng;
+    Proposal prop;
+    if (warp == NWW) {
+        make_proposal(pb, chain, cube, site, (unsigned)it, ev, rng, prop);
+        warp_line_profile(pb, sm, prop.c_new, prop.w_new, sm.g_n, sm.Lu_n, lane);
+    } else if (warp == NWW + 1) {
+        const double* prm = pb.params + ((size_t)chain * HW + site) * 3;
+        warp_line_profile(pb, sm, prm[1], prm[2], sm.g_o, sm.Lu_o, lane);
+    }
+
+    const int y0 = max(y - pb.fhh, 0), y1 = min(y + pb.fhh + 1, H);
+    const int x0 = max(x - pb.fhw, 0), x1 = min(x + pb.fhw + 1, W);
+    const int ww = x1 - x0, npos = (y1 - y0) * ww;
+    const int oy = y0 - (y - pb.fhh), ox = x0 - (x - pb.fhw);
+    const int ZL = Dp / VEC, NC = (NWW * 32) / ZL;
+    const int col = tid / ZL, zp = tid - col * ZL;
+    const bool worker = col < NC;
+    // this CTA's share of the positions
+    const int share = (npos + CS - 1) / CS;
+    const int q0 = min(cr * share, npos), q1 = min(q0 + share, npos);
+
+    T* err = (T*)pb.err + (size_t)chain * HW * Dp;
+    const T* ivc = IVCUBE ? (const T*)pb.iv + (size_t)cube * HW * Dp : nullptr;
+    const double ivs = IVCUBE ? 0.0 : pb.iv_scalar[cube];
+
+    double h[VEC], g[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
+    double f2 = 0.0;
+    if (worker) {
+        const int UN = 4;
+        for (int qb = q0 + col; qb < q1; qb += UN * NC) {
+            V ev_[UN], wv_[UN];
+            double f_[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int q = qb + u * NC;
+                if (q < q1) {
+                    const int dy = q / ww, dx = q - dy * ww;
+                    const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                    ev_[u] = *(const V*)(err + off);
+                    if (IVCUBE) wv_[u] = *(const V*)(ivc + off);
+                    f_[u] = sm.F[(oy + dy) * pb.fw + ox + dx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (qb + u * NC < q1) {
+                    double e[VEC];
+                    unpack(ev_[u], e);
+                    const double f = f_[u];
+                    if (IVCUBE) {
+                        double w_[VEC];
+                        unpack(wv_[u], w_);
+                        const double ff = f * f;
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            h[v] = fma(f, w_[v] * e[v], h[v]);
+                            g[v] = fma(ff, w_[v], g[v]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) h[v] = fma(f, e[v], h[v]);
+                        f2 = fma(f, f, f2);
+                    }
+                }
+            }
+        }
+        if (!IVCUBE) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { h[v] *= ivs; g[v] = ivs * f2; }
+        }
+    }
+    __syncthreads();                                   // profiles ready
+
+    double part[R_N];
+#pragma unroll
+    for (int j = 0; j < R_N; ++j) part[j] = 0.0;
+    double lo_v[VEC], ln_v[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { lo_v[v] = 0.0; ln_v[v] = 0.0; }
+    if (worker) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            lo_v[v] = sm.Lu_o[zp * VEC + v];
+            ln_v[v] = sm.Lu_n[zp * VEC + v];
+            const double dl = lo_v[v] - ln_v[v];
+            part[R_B] = fma(dl, h[v], part[R_B]);
+            part[R_PO] = fma(lo_v[v], h[v], part[R_PO]);
+            part[R_C] = fma(dl * dl, g[v], part[R_C]);
+            part[R_QOO] = fma(lo_v[v] * lo_v[v], g[v], part[R_QOO]);
+            part[R_QON] = fma(lo_v[v] * ln_v[v], g[v], part[R_QON]);
+            part[R_QNN] = fma(ln_v[v] * ln_v[v], g[v], part[R_QNN]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < R_N; ++j) {
+        if (j == R_A) continue;
+        const double s = warp_sum(part[j]);
+        if (lane == 0 && warp < NWW) sm.red[warp * 8 + j] = s;
+    }
+    __syncthreads();
+    // CTA totals -> slot `cr` of the leader's exchange area (second half of sm.red)
+    if (warp == NWW) {
+        double* leader_x = cluster.map_shared_rank(sm.red + 128, 0);
+#pragma unroll
+        for (int j = 0; j < R_N; ++j) {
+            if (j == R_A) continue;
+            const double s = warp_sum(lane < nwarps ? sm.red[lane * 8 + j] : 0.0);
+            if (lane == 0) leader_x[cr * 8 + j] = s;
+        }
+    }
+    cluster.sync();
+    int accepted = 0;
+    if (cr == 0 && warp == NWW) {
+        double tot[R_N];
+#pragma unroll
+        for (int j = 0; j < R_N; ++j) {
+            if (j == R_A) { tot[j] = 0.0; continue; }
+            tot[j] = warp_sum(lane < CS ? sm.red[128 + lane * 8 + j] : 0.0);
+        }
+        accepted = decide(pb, sm, chain, cube, site, prop, tot, rng, crow, lrow, ev, lane);
+        if (lane == 0) {
+            if (accepted) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+            if (pb.acc_cur) pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)accepted;
+        }
+    }
+    cluster.sync();                                    // decision in the leader's sm.bc
+    const double* bc = cluster.map_shared_rank(sm.bc, 0);
+    const int acc = bc[0] != 0.0;
+    const double r = bc[1], a = bc[3];
+    if (worker) {
+        double coef[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) coef[v] = upd_coef(a, lo_v[v], r, acc ? ln_v[v] : lo_v[v]);
+        const int UN = 4;
+        for (int qb = q0 + col; qb < q1; qb += UN * NC) {
+            V ev_[UN];
+            double f_[UN];
+            size_t off_[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int q = qb + u * NC;
+                if (q < q1) {
+                    const int dy = q / ww, dx = q - dy * ww;
+                    off_[u] = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                    ev_[u] = *(const V*)(err + off_[u]);
+                    f_[u] = sm.F[(oy + dy) * pb.fw + ox + dx];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (qb + u * NC < q1) {
+                    double e[VEC];
+                    unpack(ev_[u], e);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) e[v] = fma(f_[u], coef[v], e[v]);
+                    V o;
+                    pack(o, e);
+                    *(V*)(err + off_[u]) = o;
+                }
+            }
+        }
+    }
+    cluster.sync();                                    // nobody leaves while its sm.bc is read
+}
+
+// Remote records on large windows: a cluster per record, every CTA rebuilds both profiles and
+// adds its share of the rank-1 field.
+template <typename T>
+__global__ void __launch_bounds__(256)
+apply_records_cluster_kernel(const __grid_constant__ Problem pb, const double* rec, int n_rec) {
+    typedef typename Vec<T>::V V;
+    const int VEC = Vec<T>::N;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+    extern __shared__ double smem_raw[];
+    const double* r = rec + (size_t)(blockIdx.x / CS) * REC_N;
+    const int site = (int)r[REC_SITE];
+    if (site < 0) return;
+    const int chain = (int)r[REC_CHAIN];
+    const int W = pb.W, H = pb.H, Dp = pb.Dp;
+    const int y = site / W, x = site - y * W;
+    if (y >= pb.ty0 && y < pb.ty1 && x >= pb.tx0 && x < pb.tx1) return;      // mine
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    load_constants(sm, pb);
+    const size_t HW = (size_t)H * W;
+    double* prm = pb.params + ((size_t)chain * HW + site) * 3;
+    const double a_o = prm[0], c_o = prm[1], w_o = prm[2];
+    const double a_n = r[REC_A], c_n = r[REC_C], w_n = r[REC_W];
+    __syncthreads();
+    cluster.sync();                                        // every CTA has read the old parameters
+    const int y0 = max(max(y - pb.fhh, 0), pb.ry0), y1 = min(min(y + pb.fhh + 1, H), pb.ry1);
+    const int x0 = max(max(x - pb.fhw, 0), pb.rx0), x1 = min(min(x + pb.fhw + 1, W), pb.rx1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (y0 < y1 && x0 < x1) {
+        if (warp == 0) warp_line_profile(pb, sm, c_o, w_o, sm.g_o, sm.Lu_o, lane);
+        else if (warp == 1) warp_line_profile(pb, sm, c_n, w_n, sm.g_n, sm.Lu_n, lane);
+        __syncthreads();
+        const int ww = x1 - x0, npos = (y1 - y0) * ww;
+        const int oy = y0 - (y - pb.fhh), ox = x0 - (x - pb.fhw);
+        const int ZL = Dp / VEC, NC = blockDim.x / ZL;
+        const int col = tid / ZL, zp = tid - col * ZL;
+        const int share = (npos + CS - 1) / CS;
+        const int q0 = min(cr * share, npos), q1 = min(q0 + share, npos);
+        if (col < NC) {
+            double coef[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                coef[v] = upd_coef(a_o, sm.Lu_o[zp * VEC + v], a_n, sm.Lu_n[zp * VEC + v]);
+            T* err = (T*)pb.err + (size_t)chain * HW * Dp;
+            for (int q = q0 + col; q < q1; q += NC) {
+                const int dy = q / ww, dx = q - dy * ww;
+                const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+                double e[VEC];
+                unpack(*(const V*)(err + off), e);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                V o;
+                pack(o, e);
+                *(V*)(err + off) = o;
+            }
+        }
+    }
+    if (cr == 0 && tid == 0) {
         prm[0] = a_n; prm[1] = c_n; prm[2] = w_n;
         pb.lik_cur[(size_t)chain * HW + site] = r[REC_LIK];
         const int acc = r[REC_ACC] != 0.0;

@@ -324,6 +324,36 @@ def test_coloured_mode_vs_oracle_same_order(nat):
                    g['in_initial_parameters'], 8, 1, seed=5, jump=0.3, prior=50.0, mode='colour')
 
 
+@pytest.mark.parametrize('fsf_shape', [(13, 13), (23, 23)])
+def test_coloured_chain_per_cta_equals_launch_per_class(nat, monkeypatch, fsf_shape):
+    """Coloured mode has two schedules: one launch per colour class (few chains) and one CTA per
+    chain walking the sites in colour-class order (many chains).  Same chains, bit for bit."""
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(12)
+    D, H, W = 12, 18, 20
+    data = synthetic(D, H, W, 5)
+    fsf = port.moffat_fsf_image(fsf_shape, 0.2, fwhm_arcsec=0.8, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    mask = (rs.rand(H, W) > 0.2).astype(float)
+    out = []
+    for by_chain in ('0', '1'):
+        monkeypatch.setenv('D3D_COLOUR_BY_CHAIN', by_chain)
+        ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, mask=mask, chains=3, seed=19)
+        ctx.init_params_uniform()
+        ctx.forward(write_err=True)
+        chain = np.zeros((3, 5, H, W, 3))
+        lik = np.zeros((3, 5, H, W))
+        acc, its, _ = ctx.sweep(1, 4, mode=nat.COLOURED, refresh_every=2, min_acceptance_rate=0.0,
+                                chain_out=chain, lik_out=lik)
+        out.append((chain, lik, acc, its, ctx.get_residual()))
+    m = mask == 1
+    assert np.array_equal(out[0][0][:, 1:][:, :, m], out[1][0][:, 1:][:, :, m])
+    assert np.array_equal(out[0][1][:, 1:][:, :, m], out[1][1][:, 1:][:, :, m])
+    assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
+    assert np.array_equal(out[0][4], out[1][4])
+
+
 def test_fp32_storage_chain_close(nat):
     """float32 storage: same decisions are not required; the chain must stay close over
     a few sweeps and the residual must match its own forward model."""
@@ -501,6 +531,23 @@ def test_large_fsf_generic_kernels_vs_oracle(nat, mode):
     var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
     init = np.dstack([rs.rand(H, W) * 4, 2 + rs.rand(H, W) * 6, 0.7 + rs.rand(H, W) * 2])
     _compare_chain(nat, data, fsf, lsf, var, None, init, 6, 1, seed=17, mode=mode)
+
+
+@pytest.mark.parametrize('cluster', ['2', '8'])
+def test_cluster_split_colour_kernel_vs_oracle(nat, monkeypatch, cluster):
+    """Big windows are worked by a thread-block cluster per site (DSMEM reduction): forced here on
+    a small problem so that the oracle can follow; decisions included."""
+    monkeypatch.setenv('D3D_CLUSTER', cluster)
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(3)
+    D, H, W = 12, 17, 19
+    data = synthetic(D, H, W, 9)
+    fsf = port.moffat_fsf_image((23, 23), 0.2, fwhm_arcsec=1.2, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    init = np.dstack([rs.rand(H, W) * 4, 2 + rs.rand(H, W) * 6, 0.7 + rs.rand(H, W) * 2])
+    _compare_chain(nat, data, fsf, lsf, var, None, init, 5, 1, seed=17, mode='colour')
+    _compare_chain(nat, data, fsf, lsf, np.array([0.05 ** 2]), None, init, 4, 1, seed=18, mode='colour')
 
 
 def test_mat_fixture_chain_vs_oracle(nat):
