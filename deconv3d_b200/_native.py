@@ -25,7 +25,7 @@ SYMBOLS = [
     'd3d_forward', 'd3d_simulate', 'd3d_simulate_clean', 'd3d_get_residual', 'd3d_conv1d',
     'd3d_rtnorm', 'd3d_delta_logl', 'd3d_sweep', 'd3d_get_counters',
     'd3d_set_tile', 'd3d_tile_record_slots', 'd3d_colour_begin', 'd3d_colour_phase',
-    'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control',
+    'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control', 'd3d_chain_mean',
 ]
 RECORD_DOUBLES = 8
 
@@ -44,6 +44,8 @@ def _ptr(a):
         return None
     if isinstance(a, int):              # raw (device) address
         return ctypes.c_void_p(a)
+    if hasattr(a, 'data_ptr'):          # torch tensor
+        return ctypes.c_void_p(a.data_ptr())
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
@@ -96,6 +98,7 @@ def load():
     lib.d3d_apply_records.argtypes = [vp, vp, i64]
     lib.d3d_get_likelihoods.argtypes = [vp, vp]
     lib.d3d_get_chain_control.argtypes = [vp, vp, vp, vp]
+    lib.d3d_chain_mean.argtypes = [vp, vp, i64, i64, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('d3d_last_error',):
@@ -268,7 +271,10 @@ class Context(object):
         n_rows = 0
         for a in (chain_out, lik_out):
             if a is not None:
-                assert a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+                if hasattr(a, 'data_ptr'):          # torch tensor (device or host)
+                    assert str(a.dtype) == 'torch.float64' and a.is_contiguous()
+                else:
+                    assert a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
                 assert a.shape[0] == self.n_chains
                 n_rows = a.shape[1]
         acc = np.zeros(self.n_chains, dtype=np.int64)
@@ -318,6 +324,14 @@ class Context(object):
         act = np.zeros(self.n_chains, dtype=np.int32)
         _check(self.lib.d3d_get_chain_control(self.h, _ptr(acc), _ptr(its), _ptr(act)))
         return acc, its, act
+
+    def chain_mean(self, chain, first_row):
+        """Mean over rows [first_row:] of chain [n_chains, rows, H, W, 3] (numpy or torch tensor,
+        host or device) -> numpy [n_chains, H, W, 3]."""
+        D, H, W = self.shape
+        out = np.empty((self.n_chains, H, W, 3))
+        _check(self.lib.d3d_chain_mean(self.h, _ptr(chain), int(chain.shape[1]), int(first_row), _ptr(out)))
+        return out
 
     def counters(self):
         a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)

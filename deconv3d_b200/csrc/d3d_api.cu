@@ -13,6 +13,7 @@
 #include <string>
 #include <algorithm>
 #include <stdlib.h>
+#include <chrono>
 
 #include "../../include/deconv3d_b200.h"
 #include "d3d_kernels.cuh"
@@ -924,6 +925,14 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
                     (long long)n_rows, (long long)(row_last * keep_one_in), row_last);
     double* chain_dev = nullptr; double* lik_dev = nullptr;
     int rc = 0;
+    const bool timing = getenv("D3D_TIMING") != nullptr;       // host-side stage times on stderr
+    auto t_host = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what) {
+        if (!timing) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[d3d_sweep] %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t_host).count());
+        t_host = n;
+    };
     if (chain_out && rows_local > 0) {
         if (cudaMalloc(&chain_dev, (size_t)pb.n_chains * rows_local * HW * 3 * sizeof(double)) != cudaSuccess)
             return fail(D3D_ENOMEM, "Not enough device memory for that many iterations. Use a higher value in the keep_one_in= parameter.");
@@ -945,6 +954,7 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         colour_by_chain = whole && pb.n_chains >= (2 * sms) / 3;
         if (const char* ev = getenv("D3D_COLOUR_BY_CHAIN")) colour_by_chain = whole && atoi(ev) != 0;
     }
+    stamp("staging alloc");
     cudaEventRecord(c->ev0, c->stream);
     cudaError_t e = cudaSuccess;
     long long it = it_begin;
@@ -985,22 +995,23 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
     }
     cudaEventRecord(c->ev1, c->stream);
     if (e != cudaSuccess && !rc) rc = fail(D3D_ECUDA, "sweep launch failed: %s", cudaGetErrorString(e));
+    stamp("launches enqueued");
+    if (timing) { cudaStreamSynchronize(c->stream); stamp("kernels done"); }
 
-    // copy the recorded rows to the caller's [n_chains][n_rows] arrays
+    // copy the recorded rows to the caller's [n_chains][n_rows] arrays: one strided copy per
+    // array (row block of chain k -> rows [row_first, row_first + rows_local) of chain k)
     if (!rc && rows_local > 0) {
-        for (int k = 0; k < pb.n_chains && !rc; ++k) {
-            if (chain_dev) {
-                e = cudaMemcpyAsync(chain_out + ((size_t)k * n_rows + row_first) * HW * 3,
-                                    chain_dev + (size_t)k * rows_local * HW * 3,
-                                    (size_t)rows_local * HW * 3 * sizeof(double), cudaMemcpyDefault, c->stream);
-                if (e != cudaSuccess) rc = fail(D3D_ECUDA, "chain copy failed: %s", cudaGetErrorString(e));
-            }
-            if (lik_dev && !rc) {
-                e = cudaMemcpyAsync(lik_out + ((size_t)k * n_rows + row_first) * HW,
-                                    lik_dev + (size_t)k * rows_local * HW,
-                                    (size_t)rows_local * HW * sizeof(double), cudaMemcpyDefault, c->stream);
-                if (e != cudaSuccess) rc = fail(D3D_ECUDA, "likelihood copy failed: %s", cudaGetErrorString(e));
-            }
+        if (chain_dev) {
+            const size_t w = (size_t)rows_local * HW * 3 * sizeof(double);
+            e = cudaMemcpy2DAsync(chain_out + (size_t)row_first * HW * 3, (size_t)n_rows * HW * 3 * sizeof(double),
+                                  chain_dev, w, w, pb.n_chains, cudaMemcpyDefault, c->stream);
+            if (e != cudaSuccess) rc = fail(D3D_ECUDA, "chain copy failed: %s", cudaGetErrorString(e));
+        }
+        if (lik_dev && !rc) {
+            const size_t w = (size_t)rows_local * HW * sizeof(double);
+            e = cudaMemcpy2DAsync(lik_out + (size_t)row_first * HW, (size_t)n_rows * HW * sizeof(double),
+                                  lik_dev, w, w, pb.n_chains, cudaMemcpyDefault, c->stream);
+            if (e != cudaSuccess) rc = fail(D3D_ECUDA, "likelihood copy failed: %s", cudaGetErrorString(e));
         }
     }
     std::vector<long long> h_acc(pb.n_chains), h_it(pb.n_chains);
@@ -1010,9 +1021,12 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         cudaMemcpyAsync(h_it.data(), pb.iters, pb.n_chains * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
         cudaMemcpyAsync(&h_status, pb.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
     }
+    stamp("row copies enqueued");
     e = cudaStreamSynchronize(c->stream);
+    stamp("row copies done");
     if (chain_dev) cudaFree(chain_dev);
     if (lik_dev) cudaFree(lik_dev);
+    stamp("staging free");
     if (rc) return rc;
     if (e != cudaSuccess) return fail(D3D_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
     if (elapsed_ms) cudaEventElapsedTime(elapsed_ms, c->ev0, c->ev1);
@@ -1199,6 +1213,39 @@ extern "C" int d3d_get_chain_control(d3d_ctx* c, int64_t* accepted_out, int64_t*
     if (h_status)
         return fail(D3D_ENUMERIC, "cannot convert float NaN to integer: a NaN reached the truncated-normal sampler "
                                   "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");
+    return 0;
+}
+
+extern "C" int d3d_chain_mean(d3d_ctx* c, const double* chain, int64_t n_rows, int64_t first_row,
+                              double* mean_out) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_chain_mean before d3d_set_problem");
+    if (!chain || !mean_out) return fail(D3D_EINVAL, "d3d_chain_mean: NULL argument");
+    if (n_rows < 1 || first_row < 0 || first_row >= n_rows) return fail(D3D_EINVAL, "d3d_chain_mean: bad row range");
+    CK(cudaSetDevice(c->device));
+    const Problem& pb = c->pb;
+    const long long row_elems = (long long)pb.H * pb.W * 3;
+    const size_t out_bytes = (size_t)pb.n_chains * row_elems * sizeof(double);
+    const size_t in_bytes = (size_t)pb.n_chains * n_rows * row_elems * sizeof(double);
+    const bool in_dev = is_device_ptr(chain), out_dev = is_device_ptr(mean_out);
+    double* d_in = nullptr; double* d_out = nullptr;
+    if (!in_dev) {
+        if (cudaMalloc(&d_in, in_bytes) != cudaSuccess) return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) failed", in_bytes);
+        cudaMemcpyAsync(d_in, chain, in_bytes, cudaMemcpyHostToDevice, c->stream);
+    }
+    if (!out_dev && cudaMalloc(&d_out, out_bytes) != cudaSuccess) {
+        if (d_in) cudaFree(d_in);
+        return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) failed", out_bytes);
+    }
+    const long long n = (long long)pb.n_chains * row_elems;
+    chain_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in_dev ? chain : d_in, pb.n_chains, n_rows,
+                                                                           first_row, row_elems, out_dev ? mean_out : d_out);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && !out_dev) e = cudaMemcpyAsync(mean_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_chain_mean failed: %s", cudaGetErrorString(e));
     return 0;
 }
 

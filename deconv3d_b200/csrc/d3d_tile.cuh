@@ -393,4 +393,17 @@ apply_records_cluster_kernel(const __grid_constant__ Problem pb, const double* r
     }
 }
 
+// Posterior summary on the device (lib/run.py:581-593): mean over rows [first_row, n_rows) of a
+// chain buffer [n_chains][n_rows][HW*3]; one thread per (chain, element).
+__global__ void chain_mean_kernel(const double* chain, int n_chains, long long n_rows, long long first_row,
+                                  long long row_elems, double* mean) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_chains * row_elems) return;
+    const long long k = i / row_elems, j = i - k * row_elems;
+    const double* p = chain + ((size_t)k * n_rows + first_row) * row_elems + j;
+    double s = 0.0;
+    for (long long r = first_row; r < n_rows; ++r, p += row_elems) s += *p;
+    mean[i] = s / (double)(n_rows - first_row);
+}
+
 }  // namespace d3d

@@ -80,6 +80,7 @@ class Run(object):
         n_chains = int(extensions.pop('n_chains', 1))
         device = int(extensions.pop('device', 0))
         first_chain_id = int(extensions.pop('first_chain_id', 0))
+        chain_on_device = bool(extensions.pop('chain_on_device', False))
         if extensions:
             raise TypeError("Unknown arguments: %s" % ', '.join(sorted(extensions)))
         if mode not in ('sequential', 'coloured'):
@@ -152,9 +153,19 @@ class Run(object):
 
         # -- chain storage (lib/run.py:267-281) ---------------------------------------
         try:
-            chains = np.zeros((n_chains, n_saved, height, width, n_params))
-            likelihoods = np.zeros((n_chains, n_saved, height, width))
-        except MemoryError:
+            if chain_on_device:
+                # the chain stays in HBM; only the posterior summary and the final
+                # cubes come back (``run.chain`` copies it to the host on first access)
+                import torch
+                tdev = torch.device('cuda', device)
+                chains = torch.zeros((n_chains, n_saved, height, width, n_params),
+                                     dtype=torch.float64, device=tdev)
+                likelihoods = torch.zeros((n_chains, n_saved, height, width),
+                                          dtype=torch.float64, device=tdev)
+            else:
+                chains = np.zeros((n_chains, n_saved, height, width, n_params))
+                likelihoods = np.zeros((n_chains, n_saved, height, width))
+        except (MemoryError, RuntimeError):
             self.logger.error("Not enough RAM available for that many iterations. "
                               "Use a higher value in the keep_one_in= parameter.")
             return
@@ -179,11 +190,16 @@ class Run(object):
                 raise ValueError(
                     "Initial params MUST have (%d, %d) shape, got %s."
                     % (height, width, str(tuple(ip_shape[:2]))))
-            chains[:, 0] = initial_parameters
-            ctx.set_params(np.ascontiguousarray(chains[:, 0]))
+            first_row = np.ascontiguousarray(
+                np.broadcast_to(initial_parameters, (n_chains, height, width, n_params)), dtype=np.float64)
+            ctx.set_params(first_row)
         else:
             ctx.init_params_uniform()
-            chains[:, 0] = ctx.get_params()
+            first_row = ctx.get_params()
+        if chain_on_device:
+            chains[:, 0] = torch.from_numpy(first_row).to(tdev)
+        else:
+            chains[:, 0] = first_row
 
         # -- sweeps (lib/run.py:316-537) --------------------------------------------------
         self.logger.info("Iteration #1")
@@ -212,13 +228,21 @@ class Run(object):
         # leaves them uninitialised, lib/run.py:270); keep the initial values there
         off = self.mask != 1
         if off.any() and n_saved > 1:
-            chains[:, 1:, off] = chains[:, :1, off]
+            if chain_on_device:
+                off_t = torch.from_numpy(off).to(tdev)
+                chains[:, 1:, off_t] = chains[:, :1, off_t]
+            else:
+                chains[:, 1:, off] = chains[:, :1, off]
 
         # -- outputs (lib/run.py:539-549) ----------------------------------------------------
-        self.chains = chains
-        self.chain = chains[0]
-        self.all_likelihoods = likelihoods
-        self.likelihoods = likelihoods[0]
+        if chain_on_device:
+            self._chains_device = chains
+            self._likelihoods_device = likelihoods
+        else:
+            self.chains = chains
+            self.chain = chains[0]
+            self.all_likelihoods = likelihoods
+            self.likelihoods = likelihoods[0]
         self.parameters = self.extract_parameters()
         self.convolved_cube = Cube(data=self.simulate_convolved(shape, self.parameters),
                                    meta=self.cube.meta)
@@ -312,8 +336,24 @@ class Run(object):
         u = np.random.uniform(-np.pi / 2., np.pi / 2., size=len(parameters))
         return parameters + amplitude * np.tan(u)
 
+    def __getattr__(self, name):
+        # chain_on_device=True: the host copies of the chain are made on first access
+        if name in ('chains', 'chain', 'all_likelihoods', 'likelihoods') and \
+                '_chains_device' in self.__dict__:
+            self.chains = self._chains_device.cpu().numpy()
+            self.chain = self.chains[0]
+            self.all_likelihoods = self._likelihoods_device.cpu().numpy()
+            self.likelihoods = self.all_likelihoods[0]
+            return self.__dict__[name]
+        raise AttributeError(name)
+
     def extract_parameters(self, percentage=20.):
         """Mean of the last ``percentage`` % of the chain, per spaxel (lib/run.py:581-593)."""
+        if '_chains_device' in self.__dict__ and 'chains' not in self.__dict__:
+            rows = self._chains_device.shape[1]
+            start = (100. - percentage) * rows / 100.
+            self.parameters_all = self._ctx.chain_mean(self._chains_device, int(start))
+            return self.parameters_all[0]
         start = (100. - percentage) * self.chain.shape[0] / 100.
         return np.mean(self.chain[int(start):, ...], 0)
 

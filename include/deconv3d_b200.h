@@ -209,6 +209,13 @@ int d3d_get_likelihoods(d3d_ctx* ctx, double* lik_out);
 int d3d_get_chain_control(d3d_ctx* ctx, int64_t* accepted_out, int64_t* iterations_out,
                           int32_t* active_out);
 
+/* Posterior summary without shipping the chain to the host: mean over rows
+ * [first_row, n_rows) of chain [n_chains][n_rows][H][W][3] (host or device) ->
+ * mean_out [n_chains][H][W][3] (host or device).  extract_parameters,
+ * lib/run.py:581-593, with first_row = int((100 - percentage) * n_rows / 100). */
+int d3d_chain_mean(d3d_ctx* ctx, const double* chain, int64_t n_rows, int64_t first_row,
+                   double* mean_out);
+
 /* Introspection for benches: launches of library kernels so far, algorithmic
  * bytes of the last d3d_sweep (3*s*D*wh*ww per site update with a variance
  * cube, 2*s*D*wh*ww with a scalar variance), site updates done. */

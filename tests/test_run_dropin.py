@@ -150,3 +150,40 @@ def test_coloured_mode_and_multi_chain_run():
     res = cube.data - run.convolved_cube.data
     assert np.mean(res ** 2 / run.variance_cube) < 5.0
     assert not np.array_equal(run.chains[0, -1], run.chains[1, -1])
+
+
+def test_chain_kept_on_device_gives_the_same_outputs():
+    """``chain_on_device=True`` keeps the chain in HBM, the posterior mean
+    (extract_parameters, lib/run.py:581-593) is reduced on the device; ``run.chain`` is copied to
+    the host only when asked for."""
+    from deconv3d_b200 import Run, MUSE
+    cube = _muse_cube()
+    mask = np.ones((30, 30))
+    mask[:3, :] = 0
+    kw = dict(max_iterations=40, keep_one_in=2, seed=11, n_chains=2, mask=mask)
+    host = Run(cube, MUSE(), **kw)
+    dev = Run(cube, MUSE(), chain_on_device=True, **kw)
+    assert 'chain' not in dev.__dict__
+    np.testing.assert_allclose(dev.parameters, host.parameters, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(dev.convolved_cube.data, host.convolved_cube.data, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(dev.extract_parameters(50.), host.extract_parameters(50.), rtol=1e-13, atol=1e-13)
+    assert np.array_equal(dev.chain, host.chain)                    # fetched now
+    assert np.array_equal(dev.chains, host.chains)
+    assert np.array_equal(dev.likelihoods[1:], host.likelihoods[1:])
+    assert np.array_equal(dev.extract_parameters(), host.extract_parameters())   # host path after the fetch
+
+
+def test_chain_mean_entry_point_host_and_device_buffers():
+    import torch
+    from deconv3d_b200 import _native
+    rs = np.random.RandomState(0)
+    ctx = _native.Context(0)
+    D, H, W = 6, 5, 7
+    ctx.set_problem(rs.rand(1, D, H, W) + 1, np.ones(1), np.ones((3, 3)) / 9., None, np.zeros((1, 3)),
+                    np.array([[9., D - 1, D]]), [0, .1, .1], np.ones(1), chains_per_cube=2)
+    chain = rs.randn(2, 11, H, W, 3)
+    ref = chain[:, 4:].mean(axis=1)
+    np.testing.assert_allclose(ctx.chain_mean(chain, 4), ref, rtol=1e-13, atol=1e-14)
+    np.testing.assert_allclose(ctx.chain_mean(torch.from_numpy(chain).cuda(), 4), ref, rtol=1e-13, atol=1e-14)
+    with pytest.raises(_native.NativeError):
+        ctx.chain_mean(chain, 11)
