@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <stdlib.h>
 #include <chrono>
+#include <mutex>
+#include <unordered_map>
 
 #include "../../include/deconv3d_b200.h"
 #include "d3d_kernels.cuh"
@@ -40,6 +42,87 @@ static int fail(int code, const char* fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),        \
                         __FILE__, __LINE__);                                            \
     } while (0)
+
+// ------------------------------------------------------------------------------
+// Device-memory cache.  cudaMalloc / cudaFree of the 10-100 MB state and staging buffers cost
+// anything between 1 and 350 ms on the driver side (measured through Run(...), D3D_TIMING=1),
+// which is as much as the sweeps of a short run.  Freed blocks are therefore kept (up to
+// kPoolCap bytes per process) and handed out again to requests of a similar size; a free keeps
+// cudaFree's contract (device idle afterwards).  Everything below calls these two through the
+// cudaMalloc / cudaFree names.
+// ------------------------------------------------------------------------------
+namespace {
+struct PoolBlock { void* p; size_t bytes; int dev; };
+std::mutex g_pool_mu;
+std::vector<PoolBlock> g_pool_free;
+std::unordered_map<void*, PoolBlock> g_pool_live;
+size_t g_pool_cached = 0;
+const size_t kPoolCap = (size_t)4 << 30;
+
+cudaError_t pool_release_all_locked() {
+    for (auto& b : g_pool_free) { int cur; cudaGetDevice(&cur); if (cur != b.dev) cudaSetDevice(b.dev); (cudaFree)(b.p); if (cur != b.dev) cudaSetDevice(cur); }
+    g_pool_free.clear();
+    g_pool_cached = 0;
+    return cudaSuccess;
+}
+
+cudaError_t pool_malloc(void** out, size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = ((bytes ? bytes : 1) + 511) & ~(size_t)511;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pool_free.size(); ++i) {
+        const PoolBlock& b = g_pool_free[i];
+        if (b.dev != dev || b.bytes < want || b.bytes > want + want / 4 + ((size_t)1 << 20)) continue;
+        if (best < 0 || b.bytes < g_pool_free[best].bytes) best = i;
+    }
+    PoolBlock blk;
+    if (best >= 0) {
+        blk = g_pool_free[best];
+        g_pool_free.erase(g_pool_free.begin() + best);
+        g_pool_cached -= blk.bytes;
+    } else {
+        void* p = nullptr;
+        cudaError_t e = (cudaMalloc)(&p, want);
+        if (e != cudaSuccess) {                    // give the cache back and try once more
+            cudaGetLastError();
+            pool_release_all_locked();
+            e = (cudaMalloc)(&p, want);
+            if (e != cudaSuccess) return e;
+        }
+        blk.p = p; blk.bytes = want; blk.dev = dev;
+    }
+    g_pool_live[blk.p] = blk;
+    *out = blk.p;
+    return cudaSuccess;
+}
+
+cudaError_t pool_free(void* p) {
+    if (!p) return cudaSuccess;
+    cudaDeviceSynchronize();                       // cudaFree's contract
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_live.find(p);
+    if (it == g_pool_live.end()) return (cudaFree)(p);
+    PoolBlock blk = it->second;
+    g_pool_live.erase(it);
+    if (g_pool_cached + blk.bytes <= kPoolCap) { g_pool_free.push_back(blk); g_pool_cached += blk.bytes; return cudaSuccess; }
+    return (cudaFree)(blk.p);
+}
+}  // namespace
+#define cudaMalloc(pp, n) pool_malloc((void**)(pp), (n))
+#define cudaFree(p) pool_free((void*)(p))
+
+struct HostTimer {                      // D3D_TIMING=1: host-side stage times on stderr
+    bool on; const char* fn; std::chrono::steady_clock::time_point t;
+    explicit HostTimer(const char* f) : on(getenv("D3D_TIMING") != nullptr), fn(f), t(std::chrono::steady_clock::now()) {}
+    void operator()(const char* what) {
+        if (!on) return;
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[%s] %-22s %8.2f ms\n", fn, what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 struct d3d_ctx {
     int device = 0;
@@ -119,7 +202,9 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    HostTimer stamp("d3d_ctx_destroy");
     free_problem(c);
+    stamp("free problem");
     if (c->d_sched) cudaFree(c->d_sched);
     if (c->d_rec_stage) cudaFree(c->d_rec_stage);
     if (c->rt_x) cudaFree(c->rt_x);
@@ -222,7 +307,9 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
         return fail(D3D_EINVAL, "d3d_set_problem: bad var_kind");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    HostTimer stamp("d3d_set_problem");
     free_problem(c);
+    stamp("free previous");
     Problem& pb = c->pb;
     RtTables keep_rt = pb.rt;
     unsigned long long keep_seed = pb.seed;
@@ -265,6 +352,7 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(staged_data);
     pb.data = d_data; pb.iv = d_iv; pb.iv_scalar = d_ivs; pb.err = d_err;
+    stamp("cubes alloc + ingest");
 
     // mask -> row-major site lists (lib/run.py:553-566)
     std::vector<uint8_t> hmask((size_t)n_cubes * HW, 1);
@@ -314,6 +402,7 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     CK(cudaMemcpy(d_sites, sites.data(), sites.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ns, nsites.data(), n_cubes * sizeof(int), cudaMemcpyHostToDevice));
     pb.mask = d_mask; pb.sites = d_sites; pb.n_sites = d_ns;
+    stamp("mask + site lists");
 
     // FSF and the circular LSF kernel.  lib/convolution.py:89-160 in direct form
     // (SURVEY.md 8a-3): out[j] = sum_i line[i]*lsf[t], t = ((j-i+P/2) mod P) - half,
@@ -381,6 +470,7 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     pb.lik_cur = nullptr; pb.acc_cur = nullptr;              // allocated by d3d_set_tile
     if ((rc = dalloc(c, &c->d_lines, (size_t)pb.n_chains * cube_elems * sizeof(double)))) return rc;
 
+    stamp("small arrays + scratch");
     choose_launch(c);
     c->have_problem = true;
     return 0;

@@ -175,6 +175,7 @@ sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, in
     const int ZL = Dp / VEC, NC = (NWW * 32) / ZL;
     const int col = tid / ZL, zp = tid - col * ZL;
     const bool worker = col < NC;
+    const int stepy = NC / ww, stepx = NC - stepy * ww;
     // this CTA's share of the positions
     const int share = (npos + CS - 1) / CS;
     const int q0 = min(cr * share, npos), q1 = min(q0 + share, npos);
@@ -189,6 +190,8 @@ sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, in
     double f2 = 0.0;
     if (worker) {
         const int UN = 4;
+        // (dy, dx) of the running position advance by NC without divisions
+        int dy = (q0 + col) / ww, dx = (q0 + col) - dy * ww;
         for (int qb = q0 + col; qb < q1; qb += UN * NC) {
             V ev_[UN], wv_[UN];
             double f_[UN];
@@ -196,12 +199,13 @@ sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, in
             for (int u = 0; u < UN; ++u) {
                 const int q = qb + u * NC;
                 if (q < q1) {
-                    const int dy = q / ww, dx = q - dy * ww;
                     const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
                     ev_[u] = *(const V*)(err + off);
                     if (IVCUBE) wv_[u] = *(const V*)(ivc + off);
                     f_[u] = sm.F[(oy + dy) * pb.fw + ox + dx];
                 }
+                dx += stepx; dy += stepy;
+                if (dx >= ww) { dx -= ww; ++dy; }
             }
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
@@ -294,6 +298,7 @@ sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, in
 #pragma unroll
         for (int v = 0; v < VEC; ++v) coef[v] = upd_coef(a, lo_v[v], r, acc ? ln_v[v] : lo_v[v]);
         const int UN = 4;
+        int dy = (q0 + col) / ww, dx = (q0 + col) - dy * ww;
         for (int qb = q0 + col; qb < q1; qb += UN * NC) {
             V ev_[UN];
             double f_[UN];
@@ -302,11 +307,12 @@ sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, in
             for (int u = 0; u < UN; ++u) {
                 const int q = qb + u * NC;
                 if (q < q1) {
-                    const int dy = q / ww, dx = q - dy * ww;
                     off_[u] = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
                     ev_[u] = *(const V*)(err + off_[u]);
                     f_[u] = sm.F[(oy + dy) * pb.fw + ox + dx];
                 }
+                dx += stepx; dy += stepy;
+                if (dx >= ww) { dx -= ww; ++dy; }
             }
 #pragma unroll
             for (int u = 0; u < UN; ++u) {
