@@ -297,6 +297,10 @@ class Run(object):
         if cube.shape != data.shape:
             raise ValueError("Provided variance has not the correct shape."
                              "Expected %s, got %s" % (str(data.shape), str(cube.shape)))
+        if scalar is not None and np.isnan(data).any():
+            # NaN voxels must drop out of the chi2 sums (nansum, lib/run.py:24-27, 420-425): that
+            # needs per-voxel weights, which the scalar fast path does not carry
+            scalar = None
         return cube, scalar
 
     def _require_native_model(self):
