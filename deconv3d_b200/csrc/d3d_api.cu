@@ -1135,6 +1135,14 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
     return 0;
 }
 
+#ifdef D3D_TRACE
+extern "C" int d3d_debug_trace2(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, d3d::g_tr2, 16 * 16 * 16 * sizeof(unsigned long long));
+    return 0;
+}
+#endif
+
 #ifdef D3D_PHASE_TIMING
 extern "C" int d3d_debug_phases(unsigned long long* out16, int reset) {
     cudaDeviceSynchronize();

@@ -35,6 +35,25 @@
 
 namespace d3d {
 
+#ifdef D3D_TRACE
+// Debug build only (scratch tooling, see profiles/r01_notes.md): per-warp clock64() stamps of
+// 16 consecutive sites of chain 0.  TRD stamps behind the arrival of a value (a stamp right
+// after a bar.sync only records the issue of the barrier, not its release).
+__device__ unsigned long long g_tr2[16 * 16 * 16];
+__device__ __forceinline__ int tr_dep(double v) { return __double2hiint(v) == 0x7ff12345 ? 1 : 0; }
+#define TRW(ev)                                                                             \
+    do { if (lane == 0 && blockIdx.x == 0 && it == it0 + 3 && j >= 700 && j < 716)          \
+             g_tr2[((j - 700) * 16 + warp) * 16 + (ev)] = clock64(); } while (0)
+#define TRD(ev, v)                                                                          \
+    do { int z_ = tr_dep(v);                                                                \
+         if (lane == 0 && blockIdx.x == 0 && it == it0 + 3 && j >= 700 && j < 716)          \
+             g_tr2[((j - 700) * 16 + warp) * 16 + (ev) + z_] = clock64(); } while (0)
+#else
+#define TRW(ev)
+#define TRD(ev, v)
+#endif
+
+
 __device__ __forceinline__ void bar_arrive_named(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -184,6 +203,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
 
             PH_T0();
             if (roleW) {
+                TRW(0);
                 // ---- make the resident columns current for (y, x) --------------------
                 const int xl = x - pb.fhw;
                 int m = (grp - xl) % ngrp;
@@ -261,6 +281,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     }
                 }
                 if (warp == 0) PH_ADD(0);                        // [0] W switch + sums
+                TRD(1, h[0]);
                 bar_sync_named(2 + par, cntAll);                 // READY: profiles of site j
                 if (warp == 0) PH_ADD(1);                        // [1] W wait READY
                 double lo_v[VEC], ln_v[VEC];
@@ -283,10 +304,12 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     if ((lane & 3) == 0) sm.red[warp * 8 + warp_sum8_slot(lane)] = tot;
                 }
                 if (warp == 0) PH_ADD(2);                        // [2] W partials
+                TRW(3);
                 bar_sync_named(6, cntWB);                        // partials visible to B
                 if (warp == 0) PH_ADD(3);                        // [3] W housekeeping
                 bar_sync_named(7, cntWB);                        // decision broadcast
                 if (warp == 0) PH_ADD(4);                        // [4] W wait decision
+                TRD(4, sm.bc[1]);
                 if (active) {
                     const int acc = sm.bc[0] != 0.0;
                     const double r = sm.bc[1], a = sm.bc[3];
@@ -308,6 +331,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     }
                 }
                 if (warp == 0) PH_ADD(5);                        // [5] W update
+                TRD(5, reinterpret_cast<const double&>(ecache[0]));
                 if (j + 2 < ns) bar_arrive_named(4 + par, cntAll);   // FREE: buffers of site j
             } else if (roleB) {
                 bar_sync_named(2 + par, cntAll);
@@ -325,6 +349,8 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                 const bool oob = prop_s[7] != 0.0;
                 const double log_u = spec_s[SP_LOGU];
                 PH_ADD(7);                                       // [7] B totals
+                TRD(8, tot[0]);
+                TRD(10, a);
                 // accept test (lib/run.py:426-451)
                 double delta;
                 if (a_new != a) {
@@ -406,11 +432,13 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     if (j == ns - 1) sm.bc[2] = (double)accepted;
                 }
                 PH_ADD(8);                                       // [8] B decide
+                TRW(9);
                 bar_sync_named(7, cntWB);
                 if (j + 2 < ns) bar_arrive_named(4 + par, cntAll);
             } else if (roleA || roleP) {
                 if (j >= 2) bar_sync_named(4 + par, cntAll);     // buffers of this parity free
                 PH_ADD(9);                                       // [9] A/P wait FREE
+                TRW(12);
                 const double* prm = pb.params + ((size_t)chain * HW + site) * 3;
                 const double a = prm[0], c_old = prm[1], w_old = prm[2];
                 // Philox blocks 0..3 in lanes 0..3: draws (2b, 2b+1) of this site
@@ -524,6 +552,7 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     }
                 }
                 PH_ADD(13);                                      // [13] A/P profile
+                TRW(13);
                 __threadfence_block();
                 bar_arrive_named(2 + par, cntAll);
             }
