@@ -248,6 +248,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2x256', choices=['cfg2x256', 'cfg2', 'cfg1', 'cfg5', 'cfg4'])
     ap.add_argument('--field', type=int, default=256, help='cfg4: field side in spaxels')
+    ap.add_argument('--exchange', default='fused', choices=['fused', 'nccl'], help='cfg4: record exchange')
     ap.add_argument('--mode', default='sequential', choices=['sequential', 'coloured'])
     ap.add_argument('--chains', type=int, default=None, help='chains (or galaxies) per GPU')
     ap.add_argument('--sweeps', type=int, default=None, help='Gibbs sweeps per step')
@@ -446,7 +447,7 @@ def bench_tiled(args, rank, local_rank, world, sweeps):
     ctx.init_params_uniform()                     # Philox-addressed: identical on every rank
     ctx.forward(write_err=True)
     setup_s = time.perf_counter() - t0
-    sw = d3dist.TiledSweeper([ctx], (H, W), (fh, fw))
+    sw = d3dist.TiledSweeper([ctx], (H, W), (fh, fw), fused=args.exchange == 'fused')
     stream = sw.stream
     it = 1
     for _ in range(args.warmup):
@@ -506,7 +507,8 @@ def bench_tiled(args, rank, local_rank, world, sweeps):
         'config': {'workload': wl['desc'], 'mode': 'coloured, tiles %dx%d' % d3dist.tile_grid(H, W, world),
                    'sweeps_per_step': sweeps, 'sites_per_sweep': n_sites,
                    'phases_per_sweep': min(fh, H) * min(fw, W),
-                   'exchange': 'all-gather of %d records x 64 B per rank and phase' % sw.slots,
+                   'exchange': ('P2P stores of %d records x 64 B into every peer + flags (no collective)' if sw.fused
+                                else 'NCCL all-gather of %d records x 64 B per rank and phase') % sw.slots,
                    'l2': 'window traffic per sweep (%.0f GB) exceeds L2' % (bytes_sweep / 1e9)},
         'sweeps_per_s': value / n_sites, 'gpu_launches': int(launches),
         'clocks': clocks.summary(),

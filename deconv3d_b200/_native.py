@@ -26,6 +26,7 @@ SYMBOLS = [
     'd3d_rtnorm', 'd3d_delta_logl', 'd3d_sweep', 'd3d_get_counters',
     'd3d_set_tile', 'd3d_tile_record_slots', 'd3d_colour_begin', 'd3d_colour_phase',
     'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control', 'd3d_chain_mean',
+    'd3d_tile_fused_init', 'd3d_tile_fused_export', 'd3d_tile_fused_connect', 'd3d_colour_phase_fused',
 ]
 RECORD_DOUBLES = 8
 
@@ -99,6 +100,10 @@ def load():
     lib.d3d_get_likelihoods.argtypes = [vp, vp]
     lib.d3d_get_chain_control.argtypes = [vp, vp, vp, vp]
     lib.d3d_chain_mean.argtypes = [vp, vp, i64, i64, vp]
+    lib.d3d_tile_fused_init.argtypes = [vp, ci, ci, vp, vp]
+    lib.d3d_tile_fused_export.argtypes = [vp, vp]
+    lib.d3d_tile_fused_connect.argtypes = [vp, ci, vp, vp]
+    lib.d3d_colour_phase_fused.argtypes = [vp, i64, ci, ci, i64]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('d3d_last_error',):
@@ -311,6 +316,27 @@ class Context(object):
             records = _f64(records).reshape(-1, RECORD_DOUBLES)
             ptr, n = _ptr(records), records.shape[0]
         _check(self.lib.d3d_apply_records(self.h, ptr, n))
+
+    # fused exchange over peer memory
+    def fused_init(self, n_tiles, my_index):
+        """Returns the device address of this context's box."""
+        box = ctypes.c_void_p()
+        nbytes = ctypes.c_int64(0)
+        _check(self.lib.d3d_tile_fused_init(self.h, int(n_tiles), int(my_index), ctypes.byref(box),
+                                            ctypes.byref(nbytes)))
+        return box.value
+
+    def fused_export(self):
+        buf = (ctypes.c_ubyte * 64)()
+        _check(self.lib.d3d_tile_fused_export(self.h, buf))
+        return bytes(buf)
+
+    def fused_connect(self, index, box=None, handle=None):
+        hb = (ctypes.c_ubyte * 64).from_buffer_copy(handle) if handle is not None else None
+        _check(self.lib.d3d_tile_fused_connect(self.h, int(index), ctypes.c_void_p(box) if box else None, hb))
+
+    def colour_phase_fused(self, iteration, cy, cx, phase_index):
+        _check(self.lib.d3d_colour_phase_fused(self.h, int(iteration), int(cy), int(cx), int(phase_index)))
 
     def get_likelihoods(self):
         D, H, W = self.shape

@@ -144,6 +144,10 @@ struct d3d_ctx {
     bool colour_attr_set = false, apply_attr_set = false;
     bool cluster_attr_set = false, apply_cluster_attr_set = false;
     int* d_sites_colour = nullptr;      // [cube][max_sites] colour-class order
+    // fused tile exchange (d3d_tile.cuh): this context's box and the peers' boxes
+    void* box = nullptr; size_t box_bytes = 0; bool box_attr_set = false;
+    TileBox tb;
+    std::vector<void*> ipc_opened;
     int cluster = 0;                    // > 1: generic colour kernels work a site with a CTA cluster
     double* d_rec_stage = nullptr; size_t rec_stage_cap = 0;   // staging of host-side record buffers
     size_t sweep_smem = 0;
@@ -207,6 +211,8 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     stamp("free problem");
     if (c->d_sched) cudaFree(c->d_sched);
     if (c->d_rec_stage) cudaFree(c->d_rec_stage);
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->box) (cudaFree)(c->box);
     if (c->rt_x) cudaFree(c->rt_x);
     if (c->rt_yu) cudaFree(c->rt_yu);
     if (c->rt_nc) cudaFree(c->rt_nc);
@@ -1287,6 +1293,128 @@ extern "C" int d3d_apply_records(d3d_ctx* c, const double* records, int64_t n_re
     return 0;
 }
 
+// ---- fused exchange over peer memory (no NCCL inside the phase) ---------------------------
+static size_t box_flag_bytes() { return 256; }      // TILE_MAXW uint64 flags + the block counter, padded
+
+extern "C" int d3d_tile_fused_init(d3d_ctx* c, int n_tiles, int my_index, void** box_out, int64_t* box_bytes) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_tile_fused_init before d3d_set_problem");
+    if (!c->pb.lik_cur) return fail(D3D_ESTATE, "d3d_tile_fused_init needs d3d_set_tile");
+    if (n_tiles < 1 || n_tiles > TILE_MAXW || my_index < 0 || my_index >= n_tiles)
+        return fail(D3D_EINVAL, "d3d_tile_fused_init: 1 <= n_tiles <= %d and 0 <= my_index < n_tiles", (int)TILE_MAXW);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const Problem& pb = c->pb;
+    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
+    const long long slots = (long long)pb.n_chains * nly * nlx;
+    const size_t bytes = box_flag_bytes() + (size_t)2 * n_tiles * slots * REC_N * sizeof(double);
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    c->ipc_opened.clear();
+    if (c->box && c->box_bytes < bytes) { (cudaFree)(c->box); c->box = nullptr; }
+    if (!c->box) {
+        // a plain driver allocation (not from the cache): its handle is exported to other processes
+        if ((cudaMalloc)(&c->box, bytes) != cudaSuccess) { c->box = nullptr; return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) for the tile box failed", bytes); }
+        c->box_bytes = bytes;
+    }
+    CK(cudaMemsetAsync(c->box, 0, c->box_bytes, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    memset(&c->tb, 0, sizeof c->tb);
+    c->tb.n_tiles = n_tiles; c->tb.my_tile = my_index; c->tb.slots = slots;
+    c->tb.flags[my_index] = (unsigned long long*)c->box;
+    c->tb.inbox[my_index] = (double*)((char*)c->box + box_flag_bytes());
+    c->tb.done_counter = (unsigned int*)((char*)c->box + TILE_MAXW * sizeof(unsigned long long));
+    if (box_out) *box_out = c->box;
+    if (box_bytes) *box_bytes = (int64_t)bytes;
+    return 0;
+}
+
+extern "C" int d3d_tile_fused_export(d3d_ctx* c, unsigned char* handle64) {
+    if (!c || !c->box) return fail(D3D_ESTATE, "d3d_tile_fused_export before d3d_tile_fused_init");
+    if (!handle64) return fail(D3D_EINVAL, "handle is NULL");
+    CK(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->box));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int d3d_tile_fused_connect(d3d_ctx* c, int index, void* peer_box, const unsigned char* handle64) {
+    if (!c || !c->box) return fail(D3D_ESTATE, "d3d_tile_fused_connect before d3d_tile_fused_init");
+    if (index < 0 || index >= c->tb.n_tiles) return fail(D3D_EINVAL, "tile index %d out of range", index);
+    if (index == c->tb.my_tile) return 0;
+    CK(cudaSetDevice(c->device));
+    void* base = peer_box;
+    if (!base) {
+        if (!handle64) return fail(D3D_EINVAL, "d3d_tile_fused_connect needs a device pointer or an IPC handle");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle64, 64);
+        CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        c->ipc_opened.push_back(base);
+    } else {
+        // same process: make sure this device may store into the peer's memory
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, base) == cudaSuccess && a.type == cudaMemoryTypeDevice && a.device != c->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(D3D_ECUDA, "no peer access from device %d to device %d: %s", c->device, a.device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    c->tb.flags[index] = (unsigned long long*)base;
+    c->tb.inbox[index] = (double*)((char*)base + box_flag_bytes());
+    return 0;
+}
+
+extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int cx, int64_t phase_index) {
+    if (!c || !c->have_problem || !c->have_params || !c->have_tables)
+        return fail(D3D_ESTATE, "d3d_colour_phase_fused needs a problem, parameters and the rtnorm tables");
+    if (!c->box) return fail(D3D_ESTATE, "d3d_colour_phase_fused needs d3d_tile_fused_init");
+    const Problem& pb = c->pb;
+    for (int t = 0; t < c->tb.n_tiles; ++t)
+        if (!c->tb.flags[t]) return fail(D3D_ESTATE, "tile %d is not connected (d3d_tile_fused_connect)", t);
+    if (cy < 0 || cx < 0 || cy >= pb.fh || cx >= pb.fw) return fail(D3D_EINVAL, "colour class (%d,%d) outside the %dx%d FSF lattice", cy, cx, pb.fh, pb.fw);
+    if (iteration < 1 || iteration > 0xffffffffLL || phase_index < 0) return fail(D3D_EINVAL, "bad iteration / phase index");
+    CK(cudaSetDevice(c->device));
+    const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
+    const int n = pb.n_chains * nly * nlx;
+    if (cy < pb.H && cx < pb.W) {
+        cudaError_t e = DISPATCH(launch_colour_class, c, (long long)iteration, cy, cx, nullptr, pb.lik_cur, 1LL, 0LL);
+        if (e != cudaSuccess) return fail(D3D_ECUDA, "colour phase launch failed: %s", cudaGetErrorString(e));
+    }
+    push_records_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(pb, c->tb, cy, cx, nly, nlx, (unsigned long long)phase_index);
+    c->launches++;
+    CK(cudaGetLastError());
+    if (c->tb.n_tiles == 1) return 0;
+    if (!c->box_attr_set) {
+        cudaFuncSetAttribute(apply_box_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        cudaFuncSetAttribute(apply_box_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        cudaFuncSetAttribute(apply_box_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        cudaFuncSetAttribute(apply_box_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
+        c->box_attr_set = true;
+    }
+    const long long n_rec = (long long)c->tb.n_tiles * n;
+    const unsigned long long ph = (unsigned long long)phase_index;
+    if (c->cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_rec * c->cluster));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = c->sweep_smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (c->dtype == D3D_F64) CK(cudaLaunchKernelEx(&cfg, apply_box_kernel<double, true>, pb, c->tb, ph));
+        else CK(cudaLaunchKernelEx(&cfg, apply_box_kernel<float, true>, pb, c->tb, ph));
+    } else {
+        if (c->dtype == D3D_F64) apply_box_kernel<double, false><<<(unsigned)n_rec, 256, c->sweep_smem, c->stream>>>(pb, c->tb, ph);
+        else apply_box_kernel<float, false><<<(unsigned)n_rec, 256, c->sweep_smem, c->stream>>>(pb, c->tb, ph);
+        CK(cudaGetLastError());
+    }
+    c->launches++;
+    return 0;
+}
+
 extern "C" int d3d_get_likelihoods(d3d_ctx* c, double* lik_out) {
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_get_likelihoods before d3d_set_problem");
     const Problem& pb = c->pb;
@@ -1308,6 +1436,8 @@ extern "C" int d3d_get_chain_control(d3d_ctx* c, int64_t* accepted_out, int64_t*
     CK(cudaStreamSynchronize(c->stream));
     int h_status = 0;
     CK(cudaMemcpy(&h_status, pb.status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_status == 2)
+        return fail(D3D_ECUDA, "tile exchange timed out: a peer never published its colour phase");
     if (h_status)
         return fail(D3D_ENUMERIC, "cannot convert float NaN to integer: a NaN reached the truncated-normal sampler "
                                   "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");

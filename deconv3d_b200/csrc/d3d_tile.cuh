@@ -399,6 +399,172 @@ apply_records_cluster_kernel(const __grid_constant__ Problem pb, const double* r
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused exchange over peer memory (NVLink P2P / same device): no collective library and no host
+// round trip inside a phase.  Every context owns a "box": flags[MAXW] (uint64, monotonic phase
+// counters, one per source tile) followed by inbox[2][n_tiles][slots][REC_N] doubles (double
+// buffered by phase parity).  After its phase kernel, push_records_kernel of tile t stores its
+// records into slot t of EVERY box (its own included) and then -- last block, after a
+// system-scope fence -- publishes flags[t] = phase + 1 in every box.  The applier of the same
+// phase spins (bounded) on the flag of a record's source tile before it reads the record from
+// its own box with L2-only loads.  Two phases may overlap across GPUs, never three: a tile can
+// only start phase p+2 after its applier of p+1 saw every flag p+1, which the others publish
+// after their appliers of phase p.
+// ---------------------------------------------------------------------------
+enum { TILE_MAXW = 16 };
+
+struct TileBox {
+    int n_tiles, my_tile;
+    long long slots;                        // records per tile and phase (n_chains * lattice slots)
+    unsigned long long* flags[TILE_MAXW];   // flags array of every box (peer pointers)
+    double* inbox[TILE_MAXW];               // inbox of every box
+    unsigned int* done_counter;             // local: blocks of push_records_kernel that finished
+};
+
+__device__ __forceinline__ size_t tile_inbox_index(const TileBox& tb, int parity, int src, long long slot) {
+    return (((size_t)parity * tb.n_tiles + src) * tb.slots + slot) * REC_N;
+}
+
+__global__ void push_records_kernel(const __grid_constant__ Problem pb, const __grid_constant__ TileBox tb,
+                                    int cy, int cx, int nly, int nlx, unsigned long long phase) {
+    const int nl = nly * nlx;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < pb.n_chains * nl) {
+        const int chain = i / nl, slot = i - chain * nl;
+        const int iy = slot / nlx, ix = slot - iy * nlx;
+        const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;
+        const int cube = chain / pb.chains_per_cube;
+        const size_t HW = (size_t)pb.H * pb.W;
+        bool live = y < pb.H && x < pb.W && y >= pb.ty0 && y < pb.ty1 && x >= pb.tx0 && x < pb.tx1 &&
+                    pb.active[chain];
+        const int site = y * pb.W + x;
+        if (live) live = pb.mask[(size_t)cube * HW + site] == 1;
+        double r[REC_N];
+#pragma unroll
+        for (int k = 0; k < REC_N; ++k) r[k] = 0.0;
+        r[REC_SITE] = -1.0;
+        if (live) {
+            const double* p = pb.params + ((size_t)chain * HW + site) * 3;
+            r[REC_SITE] = (double)site; r[REC_CHAIN] = (double)chain;
+            r[REC_A] = p[0]; r[REC_C] = p[1]; r[REC_W] = p[2];
+            r[REC_LIK] = pb.lik_cur[(size_t)chain * HW + site];
+            r[REC_ACC] = (double)pb.acc_cur[(size_t)chain * HW + site];
+        }
+        const size_t at = tile_inbox_index(tb, (int)(phase & 1ull), tb.my_tile, i);
+        for (int t = 0; t < tb.n_tiles; ++t) {
+            if (t == tb.my_tile) continue;              // own records are never read back
+            double2* dst = (double2*)(tb.inbox[t] + at);
+#pragma unroll
+            for (int k = 0; k < REC_N / 2; ++k) dst[k] = make_double2(r[2 * k], r[2 * k + 1]);
+        }
+    }
+    // publish: the last block to get here raises this tile's flag in every box
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(tb.done_counter, 1u) + 1u;
+        if (done == gridDim.x) {
+            *tb.done_counter = 0u;
+            __threadfence_system();
+            for (int t = 0; t < tb.n_tiles; ++t)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(tb.flags[t] + tb.my_tile), "l"(phase + 1ull) : "memory");
+        }
+    }
+}
+
+// Waits (bounded: ~2 s) until source tile `src` has published `phase`; returns false on timeout.
+__device__ __forceinline__ bool tile_wait_flag(const TileBox& tb, int src, unsigned long long phase) {
+    const unsigned long long* f = tb.flags[tb.my_tile] + src;
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v >= phase + 1ull) return true;
+        if (clock64() - t0 > 4000000000LL) return false;
+        __nanosleep(200);
+    }
+}
+
+// Applier of the fused exchange: grid = n_tiles * slots clusters (or CTAs); record (src, slot) is
+// read from this context's own box once the source tile has published the phase.
+template <typename T, bool CLUSTER>
+__global__ void __launch_bounds__(256)
+apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ TileBox tb, unsigned long long phase) {
+    typedef typename Vec<T>::V V;
+    const int VEC = Vec<T>::N;
+    int CS = 1, cr = 0;
+    if (CLUSTER) {
+        cg::cluster_group cluster = cg::this_cluster();
+        CS = (int)cluster.num_blocks(); cr = (int)cluster.block_rank();
+    }
+    extern __shared__ double smem_raw[];
+    const long long ridx = blockIdx.x / CS;
+    const int src = (int)(ridx / tb.slots);
+    if (src == tb.my_tile) return;                           // (whole cluster)
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) s_ok = tile_wait_flag(tb, src, phase) ? 1 : 0;
+    __syncthreads();
+    if (!s_ok) { if (threadIdx.x == 0) atomicExch(pb.status, 2); return; }   // (flag state is the same for the cluster... see below)
+    const double* rp = tb.inbox[tb.my_tile] + tile_inbox_index(tb, (int)(phase & 1ull), src, ridx - (long long)src * tb.slots);
+    double r[REC_N];
+#pragma unroll
+    for (int k = 0; k < REC_N; ++k) r[k] = __ldcg(rp + k);
+    const int site = (int)r[REC_SITE];
+    if (site < 0) return;
+    const int chain = (int)r[REC_CHAIN];
+    const int W = pb.W, H = pb.H, Dp = pb.Dp;
+    const int y = site / W, x = site - y * W;
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    load_constants(sm, pb);
+    const size_t HW = (size_t)H * W;
+    double* prm = pb.params + ((size_t)chain * HW + site) * 3;
+    const double a_o = prm[0], c_o = prm[1], w_o = prm[2];
+    const double a_n = r[REC_A], c_n = r[REC_C], w_n = r[REC_W];
+    __syncthreads();
+    if (CLUSTER) cg::this_cluster().sync();                 // every CTA has read the old parameters
+    const int y0 = max(max(y - pb.fhh, 0), pb.ry0), y1 = min(min(y + pb.fhh + 1, H), pb.ry1);
+    const int x0 = max(max(x - pb.fhw, 0), pb.rx0), x1 = min(min(x + pb.fhw + 1, W), pb.rx1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (y0 < y1 && x0 < x1) {
+        if (warp == 0) warp_line_profile(pb, sm, c_o, w_o, sm.g_o, sm.Lu_o, lane);
+        else if (warp == 1) warp_line_profile(pb, sm, c_n, w_n, sm.g_n, sm.Lu_n, lane);
+        __syncthreads();
+        const int ww = x1 - x0, npos = (y1 - y0) * ww;
+        const int oy = y0 - (y - pb.fhh), ox = x0 - (x - pb.fhw);
+        const int ZL = Dp / VEC, NC = blockDim.x / ZL;
+        const int col = tid / ZL, zp = tid - col * ZL;
+        const int share = (npos + CS - 1) / CS;
+        const int q0 = min(cr * share, npos), q1 = min(q0 + share, npos);
+        if (col < NC) {
+            double coef[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                coef[v] = upd_coef(a_o, sm.Lu_o[zp * VEC + v], a_n, sm.Lu_n[zp * VEC + v]);
+            T* err = (T*)pb.err + (size_t)chain * HW * Dp;
+            for (int q = q0 + col; q < q1; q += NC) {
+                const int dy = q / ww, dx = q - dy * ww;
+                const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
+                const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
+                double e[VEC];
+                unpack(*(const V*)(err + off), e);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) e[v] = fma(f, coef[v], e[v]);
+                V o;
+                pack(o, e);
+                *(V*)(err + off) = o;
+            }
+        }
+    }
+    if (cr == 0 && tid == 0) {
+        prm[0] = a_n; prm[1] = c_n; prm[2] = w_n;
+        pb.lik_cur[(size_t)chain * HW + site] = r[REC_LIK];
+        const int acc = r[REC_ACC] != 0.0;
+        pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+        if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+    }
+}
+
 // Posterior summary on the device (lib/run.py:581-593): mean over rows [first_row, n_rows) of a
 // chain buffer [n_chains][n_rows][HW*3]; one thread per (chain, element).
 __global__ void chain_mean_kernel(const double* chain, int n_chains, long long n_rows, long long first_row,

@@ -129,7 +129,7 @@ class TiledSweeper(object):
     addressed by (seed, chain, sweep, site), not by who draws them.
     """
 
-    def __init__(self, contexts, field_hw, fsf_hw, group=None, use_torch=True):
+    def __init__(self, contexts, field_hw, fsf_hw, group=None, use_torch=True, fused=False):
         self.ctxs = list(contexts)
         self.H, self.W = int(field_hw[0]), int(field_hw[1])
         self.fh, self.fw = int(fsf_hw[0]), int(fsf_hw[1])
@@ -170,9 +170,52 @@ class TiledSweeper(object):
             self.local = np.empty((self.nlocal * self.slots, RECORD_DOUBLES))
             self.all = self.local
         self.exchanges = 0
+        self.fused = bool(fused) and self.n_tiles > 1
+        self.n_classes = min(self.fh, self.H) * min(self.fw, self.W)
+        if self.fused:
+            self._connect_boxes()
+
+    def _connect_boxes(self):
+        """Fused exchange (include/deconv3d_b200.h): every context stores its records straight
+        into the boxes of all the others -- device addresses inside this process, CUDA IPC handles
+        across the ranks -- and its applier waits on flags in its own box.  No collective and no
+        host synchronisation inside a phase."""
+        if not self.device_records:
+            raise ValueError('the fused exchange needs device contexts')
+        if self.nlocal > 1:
+            # several tiles on one GPU (tests): each context keeps its own stream, their kernels
+            # must be able to run side by side (an applier spins until its peers have pushed)
+            for ctx in self.ctxs:
+                ctx.set_stream(0)
+        first = self.rank * self.nlocal
+        boxes = [ctx.fused_init(self.n_tiles, first + i) for i, ctx in enumerate(self.ctxs)]
+        handles = [[ctx.fused_export() for ctx in self.ctxs]]
+        if self.world > 1:
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, handles[0], group=self.group)
+            handles = gathered
+        for i, ctx in enumerate(self.ctxs):
+            for g in range(self.n_tiles):
+                r, k = divmod(g, self.nlocal)
+                if g == first + i:
+                    continue
+                if r == self.rank:
+                    ctx.fused_connect(g, box=boxes[k])
+                else:
+                    ctx.fused_connect(g, handle=handles[r][k])
+        for ctx in self.ctxs:
+            ctx.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)          # nobody pushes into a box that is not ready
 
     # -- one colour phase on every local tile, then the exchange, then the appliers --
     def _phase(self, it, cy, cx):
+        if self.fused:
+            phase = it * self.n_classes + cy * min(self.fw, self.W) + cx
+            for ctx in self.ctxs:
+                ctx.colour_phase_fused(it, cy, cx, phase)
+            self.exchanges += 1
+            return
         nb = self.slots * RECORD_DOUBLES * 8
         for i, ctx in enumerate(self.ctxs):
             if self.device_records:

@@ -201,6 +201,25 @@ int d3d_colour_phase(d3d_ctx* ctx, int64_t iteration, int cy, int cx, double* re
 /* Applies the records of OTHER contexts (own and empty ones are skipped):
  * parameters, delta-logL, accepted_count and the residual inside the region. */
 int d3d_apply_records(d3d_ctx* ctx, const double* records, int64_t n_records);
+/* Fused exchange: the records go straight into the peers' memory (NVLink P2P
+ * stores from the kernel, or plain stores when the tiles share a device) and
+ * the applier of a phase waits on per-tile flags in its own memory -- no
+ * collective library and no host round trip inside a phase.
+ *   d3d_tile_fused_init    allocates this context's box for n_tiles tiles
+ *                          (box_out: its device address, for peers in the
+ *                          same process)
+ *   d3d_tile_fused_export  64-byte CUDA IPC handle of the box (peers in other
+ *                          processes)
+ *   d3d_tile_fused_connect box of tile `index`: device address or IPC handle
+ *   d3d_colour_phase_fused phase kernel + push of the records + applier;
+ *                          phase_index must grow by one per call and be the
+ *                          same on every tile (iteration * n_classes + class)
+ * A peer that never publishes its phase makes the applier give up after ~2 s
+ * (reported as D3D_ECUDA by d3d_get_chain_control). */
+int d3d_tile_fused_init(d3d_ctx* ctx, int n_tiles, int my_index, void** box_out, int64_t* box_bytes);
+int d3d_tile_fused_export(d3d_ctx* ctx, unsigned char* handle64);
+int d3d_tile_fused_connect(d3d_ctx* ctx, int index, void* peer_box, const unsigned char* handle64);
+int d3d_colour_phase_fused(d3d_ctx* ctx, int64_t iteration, int cy, int cx, int64_t phase_index);
 /* Latest delta-logL of every site [n_chains][H][W] (the row lib/run.py:430-432
  * would store); tile mode only. */
 int d3d_get_likelihoods(d3d_ctx* ctx, double* lik_out);

@@ -46,7 +46,7 @@ def _single(nat, prob, chains, n_it, dtype=None):
     return chain, lik, acc, ctx.get_residual()
 
 
-def _tiled(nat, prob, chains, n_it, n_tiles, dtype=None, refresh_every=0):
+def _tiled(nat, prob, chains, n_it, n_tiles, dtype=None, refresh_every=0, fused=False):
     from deconv3d_b200 import dist
     data, var, fsf, lsf, mask, init = prob
     D, H, W = data.shape
@@ -56,7 +56,7 @@ def _tiled(nat, prob, chains, n_it, n_tiles, dtype=None, refresh_every=0):
         ctx.set_params(np.broadcast_to(init, (chains, H, W, 3)))
         ctx.forward(write_err=True)
         ctxs.append(ctx)
-    sw = dist.TiledSweeper(ctxs, (H, W), fsf.shape)
+    sw = dist.TiledSweeper(ctxs, (H, W), fsf.shape, fused=fused)
     chain = np.zeros((chains, n_it + 1, H, W, 3))
     lik = np.zeros((chains, n_it + 1, H, W))
     acc, its = sw.sweep(1, n_it, refresh_every=refresh_every, chain_out=chain, lik_out=lik)
@@ -94,6 +94,26 @@ def test_tiling_large_fsf_generic_kernel(nat):
     chain, lik, acc, res, partial, sw, regions = _tiled(nat, prob, 1, 2, 4)
     m = prob[4] == 1
     assert np.array_equal(chain[:, 1:][:, :, m], chain1[:, 1:][:, :, m])
+    assert np.array_equal(acc, acc1)
+    for r in res:
+        np.testing.assert_allclose(r, res1, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('case', ['rowsite-13x13', 'cluster-41x41'])
+def test_fused_peer_memory_exchange_equals_one_context(nat, case):
+    """The records go straight into the other tiles' boxes and the appliers wait on flags: no
+    collective, no host round trip per phase (here the tiles share one GPU, each on its own
+    stream; on a multi-GPU box the same stores travel over NVLink)."""
+    if case == 'rowsite-13x13':
+        prob, chains, n_it, n_tiles = _problem(16, 30, 34, (13, 13), 3), 2, 3, 3
+    else:
+        prob, chains, n_it, n_tiles = _problem(64, 44, 50, (41, 41), 5), 1, 2, 2
+    chain1, lik1, acc1, res1 = _single(nat, prob, chains, n_it)
+    chain, lik, acc, res, partial, sw, regions = _tiled(nat, prob, chains, n_it, n_tiles, fused=True)
+    m = prob[4] == 1
+    assert sw.fused
+    assert np.array_equal(chain[:, 1:][:, :, m], chain1[:, 1:][:, :, m])
+    assert np.array_equal(lik[:, 1:][:, :, m], lik1[:, 1:][:, :, m])
     assert np.array_equal(acc, acc1)
     for r in res:
         np.testing.assert_allclose(r, res1, rtol=0, atol=1e-9)
