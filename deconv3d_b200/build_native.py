@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libdeconv3d_b200.so')
 SOURCES = [os.path.join(CSRC, 'd3d_api.cu')]
-DEPS = SOURCES + [os.path.join(CSRC, 'd3d_kernels.cuh'), os.path.join(CSRC, 'd3d_rng.cuh'),
-                  os.path.join(os.path.dirname(HERE), 'include', 'deconv3d_b200.h')]
+DEPS = SOURCES + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))) + \
+    [os.path.join(os.path.dirname(HERE), 'include', 'deconv3d_b200.h')]
 
 
 def find_nvcc():

@@ -122,38 +122,18 @@ __global__ void apply_records_kernel(const __grid_constant__ Problem pb, const d
 // evaluate the proposal and both line profiles redundantly (deterministic, D values).
 // grid = (lattice slots * cluster size, chains), cluster = (CS, 1, 1).
 // ---------------------------------------------------------------------------
+// One site worked by the calling cluster (constants already in shared memory, every CTA of the
+// cluster running).  8 window warps + 2 scalar warps per CTA.
 template <typename T, bool IVCUBE>
-__global__ void __launch_bounds__(320)
-sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, int cy, int cx, int nlx,
-                            double* crow_base, double* lrow_base, long long rows_local,
-                            long long row_local) {
+__device__ __forceinline__ void cluster_site_update(const Problem& pb, const Smem& sm, cg::cluster_group& cluster,
+                                                    int CS, int cr, int chain, int cube, int site, long long it,
+                                                    double* crow, double* lrow) {
     typedef typename Vec<T>::V V;
     const int VEC = Vec<T>::N;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int CS = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
-    extern __shared__ double smem_raw[];
-    Smem sm;
-    carve(sm, smem_raw, pb);
-    const int chain = blockIdx.y;
-    const int cube = chain / pb.chains_per_cube;
-    const int slot = blockIdx.x / CS;
-    const int iy = slot / nlx, ix = slot - iy * nlx;
-    const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;
-    // (every exit below is taken by the whole cluster)
-    if (y >= pb.H || x >= pb.W) return;
-    if (y < pb.ty0 || y >= pb.ty1 || x < pb.tx0 || x >= pb.tx1) return;
-    if (!pb.active[chain]) return;
     const int W = pb.W, H = pb.H, Dp = pb.Dp;
-    const int site = y * W + x;
+    const int y = site / W, x = site - y * W;
     const size_t HW = (size_t)H * W;
-    if (pb.mask[(size_t)cube * HW + site] != 1) return;
-    load_constants(sm, pb);
-    __syncthreads();
-    cluster.sync();                                    // every CTA of the cluster is running (DSMEM)
-    double* crow = crow_base ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3 : nullptr;
-    double* lrow = lrow_base ? lrow_base + ((size_t)chain * rows_local + row_local) * HW + site : nullptr;
     EvalReq ev; ev.enabled = 0; ev.out = nullptr;
-
     // 8 window warps + 2 scalar warps (proposal / new profile / decision, old profile): the
     // window loads start at once instead of waiting behind the transcendental chains
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -329,6 +309,36 @@ sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, in
         }
     }
     cluster.sync();                                    // nobody leaves while its sm.bc is read
+}
+
+template <typename T, bool IVCUBE>
+__global__ void __launch_bounds__(320)
+sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, int cy, int cx, int nlx,
+                            double* crow_base, double* lrow_base, long long rows_local,
+                            long long row_local) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
+    extern __shared__ double smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    const int chain = blockIdx.y;
+    const int cube = chain / pb.chains_per_cube;
+    const int slot = blockIdx.x / CS;
+    const int iy = slot / nlx, ix = slot - iy * nlx;
+    const int y = cy + iy * pb.fh, x = cx + ix * pb.fw;
+    // (every exit below is taken by the whole cluster)
+    if (y >= pb.H || x >= pb.W) return;
+    if (y < pb.ty0 || y >= pb.ty1 || x < pb.tx0 || x >= pb.tx1) return;
+    if (!pb.active[chain]) return;
+    const int site = y * pb.W + x;
+    const size_t HW = (size_t)pb.H * pb.W;
+    if (pb.mask[(size_t)cube * HW + site] != 1) return;
+    load_constants(sm, pb);
+    __syncthreads();
+    cluster.sync();                                    // every CTA of the cluster is running (DSMEM)
+    double* crow = crow_base ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3 : nullptr;
+    double* lrow = lrow_base ? lrow_base + ((size_t)chain * rows_local + row_local) * HW + site : nullptr;
+    cluster_site_update<T, IVCUBE>(pb, sm, cluster, CS, cr, chain, cube, site, it, crow, lrow);
 }
 
 // Remote records on large windows: a cluster per record, every CTA rebuilds both profiles and
