@@ -91,8 +91,10 @@ __global__ void apply_records_kernel(const __grid_constant__ Problem pb, const d
             for (int v = 0; v < VEC; ++v)
                 coef[v] = upd_coef(a_o, sm.Lu_o[zp * VEC + v], a_n, sm.Lu_n[zp * VEC + v]);
             T* err = (T*)pb.err + (size_t)chain * HW * Dp;
-            for (int q = col; q < npos; q += NC) {
-                const int dy = q / ww, dx = q - dy * ww;
+            const int stepy = NC / ww, stepx = NC - stepy * ww;
+            int dy = col / ww, dx = col - dy * ww;          // running position, advanced without divisions
+            for (int q = col; q < npos; q += NC, dx += stepx, dy += stepy) {
+                if (dx >= ww) { dx -= ww; ++dy; }
                 const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
                 const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
                 double e[VEC];
@@ -386,8 +388,10 @@ apply_records_cluster_kernel(const __grid_constant__ Problem pb, const double* r
             for (int v = 0; v < VEC; ++v)
                 coef[v] = upd_coef(a_o, sm.Lu_o[zp * VEC + v], a_n, sm.Lu_n[zp * VEC + v]);
             T* err = (T*)pb.err + (size_t)chain * HW * Dp;
-            for (int q = q0 + col; q < q1; q += NC) {
-                const int dy = q / ww, dx = q - dy * ww;
+            const int stepy = NC / ww, stepx = NC - stepy * ww;
+            int dy = (q0 + col) / ww, dx = (q0 + col) - dy * ww;
+            for (int q = q0 + col; q < q1; q += NC, dx += stepx, dy += stepy) {
+                if (dx >= ww) { dx -= ww; ++dy; }
                 const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
                 const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
                 double e[VEC];
@@ -552,8 +556,10 @@ apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ Til
             for (int v = 0; v < VEC; ++v)
                 coef[v] = upd_coef(a_o, sm.Lu_o[zp * VEC + v], a_n, sm.Lu_n[zp * VEC + v]);
             T* err = (T*)pb.err + (size_t)chain * HW * Dp;
-            for (int q = q0 + col; q < q1; q += NC) {
-                const int dy = q / ww, dx = q - dy * ww;
+            const int stepy = NC / ww, stepx = NC - stepy * ww;
+            int dy = (q0 + col) / ww, dx = (q0 + col) - dy * ww;
+            for (int q = q0 + col; q < q1; q += NC, dx += stepx, dy += stepy) {
+                if (dx >= ww) { dx -= ww; ++dy; }
                 const size_t off = ((size_t)(y0 + dy) * W + (x0 + dx)) * Dp + zp * VEC;
                 const double f = sm.F[(oy + dy) * pb.fw + ox + dx];
                 double e[VEC];
