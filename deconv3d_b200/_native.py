@@ -26,7 +26,7 @@ SYMBOLS = [
     'd3d_rtnorm', 'd3d_delta_logl', 'd3d_sweep', 'd3d_get_counters',
     'd3d_set_tile', 'd3d_tile_record_slots', 'd3d_colour_begin', 'd3d_colour_phase',
     'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control', 'd3d_chain_mean',
-    'd3d_tile_fused_init', 'd3d_tile_fused_export', 'd3d_tile_fused_connect', 'd3d_colour_phase_fused',
+    'd3d_tile_fused_init', 'd3d_tile_fused_export', 'd3d_tile_fused_connect', 'd3d_colour_phase_fused', 'd3d_sweep_fused',
 ]
 RECORD_DOUBLES = 8
 
@@ -104,6 +104,7 @@ def load():
     lib.d3d_tile_fused_export.argtypes = [vp, vp]
     lib.d3d_tile_fused_connect.argtypes = [vp, ci, vp, vp]
     lib.d3d_colour_phase_fused.argtypes = [vp, i64, ci, ci, i64]
+    lib.d3d_sweep_fused.argtypes = [vp, i64, i64, cd]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ('d3d_last_error',):
@@ -337,6 +338,10 @@ class Context(object):
 
     def colour_phase_fused(self, iteration, cy, cx, phase_index):
         _check(self.lib.d3d_colour_phase_fused(self.h, int(iteration), int(cy), int(cx), int(phase_index)))
+
+    def sweep_fused(self, first_iteration, n_iterations, min_acceptance_rate=0.0):
+        _check(self.lib.d3d_sweep_fused(self.h, int(first_iteration), int(n_iterations),
+                                        float(min_acceptance_rate)))
 
     def get_likelihoods(self):
         D, H, W = self.shape

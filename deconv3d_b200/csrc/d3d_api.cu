@@ -1415,6 +1415,21 @@ extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int
     return 0;
 }
 
+extern "C" int d3d_sweep_fused(d3d_ctx* c, int64_t first_iteration, int64_t n_iterations, double min_acceptance_rate) {
+    if (!c || !c->box) return fail(D3D_ESTATE, "d3d_sweep_fused needs d3d_tile_fused_init");
+    if (first_iteration < 1 || n_iterations < 0) return fail(D3D_EINVAL, "bad iteration range");
+    const Problem& pb = c->pb;
+    const int ncy = std::min(pb.fh, pb.H), ncx = std::min(pb.fw, pb.W);
+    for (int64_t it = first_iteration; it < first_iteration + n_iterations; ++it) {
+        int rc = d3d_colour_begin(c, it, min_acceptance_rate);
+        if (rc) return rc;
+        for (int cy = 0; cy < ncy; ++cy)
+            for (int cx = 0; cx < ncx; ++cx)
+                if ((rc = d3d_colour_phase_fused(c, it, cy, cx, it * ncy * ncx + (int64_t)cy * ncx + cx))) return rc;
+    }
+    return 0;
+}
+
 extern "C" int d3d_get_likelihoods(d3d_ctx* c, double* lik_out) {
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_get_likelihoods before d3d_set_problem");
     const Problem& pb = c->pb;

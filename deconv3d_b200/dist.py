@@ -252,11 +252,16 @@ class TiledSweeper(object):
         chain, identical on every rank."""
         lead = self.ctxs[0]
         for it in range(int(first_iteration), int(first_iteration + n_iterations)):
-            for ctx in self.ctxs:
-                ctx.colour_begin(it, min_acceptance_rate)
-            for cy in range(min(self.fh, self.H)):
-                for cx in range(min(self.fw, self.W)):
-                    self._phase(it, cy, cx)
+            if self.fused and self.nlocal == 1:
+                # one context per process: the whole iteration is enqueued by the library
+                lead.sweep_fused(it, 1, min_acceptance_rate)
+                self.exchanges += self.n_classes
+            else:
+                for ctx in self.ctxs:
+                    ctx.colour_begin(it, min_acceptance_rate)
+                for cy in range(min(self.fh, self.H)):
+                    for cx in range(min(self.fw, self.W)):
+                        self._phase(it, cy, cx)
             if it % keep_one_in == 0:
                 row = it // keep_one_in
                 if chain_out is not None:

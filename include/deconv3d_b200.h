@@ -220,6 +220,11 @@ int d3d_tile_fused_init(d3d_ctx* ctx, int n_tiles, int my_index, void** box_out,
 int d3d_tile_fused_export(d3d_ctx* ctx, unsigned char* handle64);
 int d3d_tile_fused_connect(d3d_ctx* ctx, int index, void* peer_box, const unsigned char* handle64);
 int d3d_colour_phase_fused(d3d_ctx* ctx, int64_t iteration, int cy, int cx, int64_t phase_index);
+/* Whole iterations of the fused tiled sweep, enqueued without returning to the
+ * caller between phases (d3d_colour_begin + every class with
+ * phase_index = iteration * n_classes + class). */
+int d3d_sweep_fused(d3d_ctx* ctx, int64_t first_iteration, int64_t n_iterations,
+                    double min_acceptance_rate);
 /* Latest delta-logL of every site [n_chains][H][W] (the row lib/run.py:430-432
  * would store); tile mode only. */
 int d3d_get_likelihoods(d3d_ctx* ctx, double* lik_out);
