@@ -29,6 +29,7 @@ SYMBOLS = [
     'd3d_tile_fused_init', 'd3d_tile_fused_export', 'd3d_tile_fused_connect', 'd3d_colour_phase_fused', 'd3d_sweep_fused',
 ]
 RECORD_DOUBLES = 8
+ABI_VERSION = 2          # D3D_ABI_VERSION of include/deconv3d_b200.h
 
 
 class NativeError(RuntimeError):
@@ -109,8 +110,9 @@ def load():
         fn = getattr(lib, name)
         if name not in ('d3d_last_error',):
             fn.restype = ci
-    if lib.d3d_abi_version() != 2:
-        raise NativeError(EINVAL, 'libdeconv3d_b200.so has ABI %d, expected 2' % lib.d3d_abi_version())
+    if lib.d3d_abi_version() != ABI_VERSION:
+        raise NativeError(EINVAL, 'libdeconv3d_b200.so has ABI %d, expected %d'
+                          % (lib.d3d_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -21,9 +21,10 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     declared = set(re.findall(r'\b(d3d_[a-z0-9_]+)\s*\(', header))
     assert declared, 'no declarations found in the header'
     assert declared == set(_native.SYMBOLS)
+    assert int(re.search(r'#define D3D_ABI_VERSION (\d+)', header).group(1)) == _native.ABI_VERSION
     for name in declared:
         assert hasattr(lib, name), 'library does not export %s' % name
-    assert _native.load().d3d_abi_version() == 2
+    assert _native.load().d3d_abi_version() == _native.ABI_VERSION
 
 
 def test_no_silent_cpu_fallback_without_gpu():
