@@ -48,8 +48,8 @@ static int fail(int code, const char* fmt, ...) {
 // anything between 1 and 350 ms on the driver side (measured through Run(...), D3D_TIMING=1),
 // which is as much as the sweeps of a short run.  Freed blocks are therefore kept (up to
 // kPoolCap bytes per process) and handed out again to requests of a similar size; a free keeps
-// cudaFree's contract (device idle afterwards).  Everything below calls these two through the
-// cudaMalloc / cudaFree names.
+// cudaFree's contract (device idle afterwards).  Everything below allocates through dev_malloc /
+// dev_free; the few plain cudaMalloc calls left are deliberate (memory exported by IPC handle).
 // ------------------------------------------------------------------------------
 namespace {
 struct PoolBlock { void* p; size_t bytes; int dev; };
@@ -60,7 +60,7 @@ size_t g_pool_cached = 0;
 const size_t kPoolCap = (size_t)4 << 30;
 
 cudaError_t pool_release_all_locked() {
-    for (auto& b : g_pool_free) { int cur; cudaGetDevice(&cur); if (cur != b.dev) cudaSetDevice(b.dev); (cudaFree)(b.p); if (cur != b.dev) cudaSetDevice(cur); }
+    for (auto& b : g_pool_free) { int cur; cudaGetDevice(&cur); if (cur != b.dev) cudaSetDevice(b.dev); cudaFree(b.p); if (cur != b.dev) cudaSetDevice(cur); }
     g_pool_free.clear();
     g_pool_cached = 0;
     return cudaSuccess;
@@ -84,11 +84,11 @@ cudaError_t pool_malloc(void** out, size_t bytes) {
         g_pool_cached -= blk.bytes;
     } else {
         void* p = nullptr;
-        cudaError_t e = (cudaMalloc)(&p, want);
+        cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) {                    // give the cache back and try once more
             cudaGetLastError();
             pool_release_all_locked();
-            e = (cudaMalloc)(&p, want);
+            e = cudaMalloc(&p, want);
             if (e != cudaSuccess) return e;
         }
         blk.p = p; blk.bytes = want; blk.dev = dev;
@@ -103,15 +103,16 @@ cudaError_t pool_free(void* p) {
     cudaDeviceSynchronize();                       // cudaFree's contract
     std::lock_guard<std::mutex> lk(g_pool_mu);
     auto it = g_pool_live.find(p);
-    if (it == g_pool_live.end()) return (cudaFree)(p);
+    if (it == g_pool_live.end()) return cudaFree(p);
     PoolBlock blk = it->second;
     g_pool_live.erase(it);
     if (g_pool_cached + blk.bytes <= kPoolCap) { g_pool_free.push_back(blk); g_pool_cached += blk.bytes; return cudaSuccess; }
-    return (cudaFree)(blk.p);
+    return cudaFree(blk.p);
 }
 }  // namespace
-#define cudaMalloc(pp, n) pool_malloc((void**)(pp), (n))
-#define cudaFree(p) pool_free((void*)(p))
+template <typename P>
+static cudaError_t dev_malloc(P** p, size_t bytes) { return pool_malloc((void**)p, bytes); }
+static cudaError_t dev_free(void* p) { return pool_free(p); }
 
 struct HostTimer {                      // D3D_TIMING=1: host-side stage times on stderr
     bool on; const char* fn; std::chrono::steady_clock::time_point t;
@@ -160,16 +161,16 @@ struct d3d_ctx {
 template <typename P>
 static int dalloc(d3d_ctx* c, P** p, size_t bytes) {
     void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+    cudaError_t e = dev_malloc(&q, bytes ? bytes : 1);
     if (e != cudaSuccess)
-        return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return fail(D3D_ENOMEM, "dev_malloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     c->allocs.push_back(q);
     *p = (P*)q;
     return 0;
 }
 
 static void free_problem(d3d_ctx* c) {
-    for (void* p : c->allocs) cudaFree(p);
+    for (void* p : c->allocs) dev_free(p);
     c->allocs.clear();
     c->d_lines = nullptr;
     c->have_problem = false;
@@ -209,13 +210,13 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     HostTimer stamp("d3d_ctx_destroy");
     free_problem(c);
     stamp("free problem");
-    if (c->d_sched) cudaFree(c->d_sched);
-    if (c->d_rec_stage) cudaFree(c->d_rec_stage);
+    if (c->d_sched) dev_free(c->d_sched);
+    if (c->d_rec_stage) dev_free(c->d_rec_stage);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
-    if (c->box) (cudaFree)(c->box);
-    if (c->rt_x) cudaFree(c->rt_x);
-    if (c->rt_yu) cudaFree(c->rt_yu);
-    if (c->rt_nc) cudaFree(c->rt_nc);
+    if (c->box) cudaFree(c->box);
+    if (c->rt_x) dev_free(c->rt_x);
+    if (c->rt_yu) dev_free(c->rt_yu);
+    if (c->rt_nc) dev_free(c->rt_nc);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);
@@ -245,18 +246,18 @@ static int ingest(d3d_ctx* c, const double* src_any, const double* nan_src_dev, 
     const Problem& pb = c->pb;
     size_t cnt = (size_t)n * pb.D * pb.H * pb.W;
     double* stage = nullptr;
-    CK(cudaMalloc(&stage, cnt * sizeof(double)));
+    CK(dev_malloc(&stage, cnt * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(stage, src_any, cnt * sizeof(double), cudaMemcpyDefault, c->stream);
-    if (e != cudaSuccess) { cudaFree(stage); return fail(D3D_ECUDA, "copy of cube failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { dev_free(stage); return fail(D3D_ECUDA, "copy of cube failed: %s", cudaGetErrorString(e)); }
     long long blocks = (long long)n * pb.H * ((pb.Dp + 31) / 32) * ((pb.W + 31) / 32);
     ingest_kernel<T><<<(unsigned)blocks, 256, 0, c->stream>>>(stage, nan_src_dev, (T*)dst, n, pb.D,
                                                               pb.Dp, pb.H, pb.W, mode);
     c->launches++;
     e = cudaGetLastError();
-    if (e != cudaSuccess) { cudaFree(stage); return fail(D3D_ECUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { dev_free(stage); return fail(D3D_ECUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
     if (staged_out) { *staged_out = stage; return 0; }
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(stage);
+    dev_free(stage);
     return 0;
 }
 
@@ -344,19 +345,19 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     if (rc) return rc;
     double* d_ivs = nullptr;
     if (pb.var_is_cube) {
-        if ((rc = dalloc(c, &d_iv, (size_t)n_cubes * cube_elems * c->elem()))) { cudaFree(staged_data); return rc; }
+        if ((rc = dalloc(c, &d_iv, (size_t)n_cubes * cube_elems * c->elem()))) { dev_free(staged_data); return rc; }
         if (c->dtype == D3D_F64) rc = ingest<double>(c, var, staged_data, d_iv, n_cubes, 1, nullptr);
         else rc = ingest<float>(c, var, staged_data, d_iv, n_cubes, 1, nullptr);
-        if (rc) { cudaFree(staged_data); return rc; }
+        if (rc) { dev_free(staged_data); return rc; }
     } else {
         std::vector<double> hv(n_cubes);
         CK(cudaMemcpy(hv.data(), var, n_cubes * sizeof(double), cudaMemcpyDefault));
         for (auto& v : hv) v = 1.0 / v;
-        if ((rc = dalloc(c, &d_ivs, n_cubes * sizeof(double)))) { cudaFree(staged_data); return rc; }
+        if ((rc = dalloc(c, &d_ivs, n_cubes * sizeof(double)))) { dev_free(staged_data); return rc; }
         CK(cudaMemcpy(d_ivs, hv.data(), n_cubes * sizeof(double), cudaMemcpyHostToDevice));
     }
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(staged_data);
+    dev_free(staged_data);
     pb.data = d_data; pb.iv = d_iv; pb.iv_scalar = d_ivs; pb.err = d_err;
     stamp("cubes alloc + ingest");
 
@@ -503,9 +504,9 @@ extern "C" int d3d_set_rtnorm_tables(d3d_ctx* c, const double* x, int nx, const 
         return fail(D3D_EINVAL, "rtnorm tables must have 4002/4001/8961 entries (lib/rtnorm.py:227-2681)");
     CK(cudaSetDevice(c->device));
     if (!c->rt_x) {
-        CK(cudaMalloc(&c->rt_x, nx * sizeof(double)));
-        CK(cudaMalloc(&c->rt_yu, nyu * sizeof(double)));
-        CK(cudaMalloc(&c->rt_nc, nncell * sizeof(int)));
+        CK(dev_malloc(&c->rt_x, nx * sizeof(double)));
+        CK(dev_malloc(&c->rt_yu, nyu * sizeof(double)));
+        CK(dev_malloc(&c->rt_nc, nncell * sizeof(int)));
     }
     CK(cudaMemcpy(c->rt_x, x, nx * sizeof(double), cudaMemcpyDefault));
     CK(cudaMemcpy(c->rt_yu, yu, nyu * sizeof(double), cudaMemcpyDefault));
@@ -652,16 +653,16 @@ static int forward_common(d3d_ctx* c, const double* params_any, int convolve, do
     double* d_params = pb.params;
     double* tmp_params = nullptr;
     if (params_any) {
-        CK(cudaMalloc(&tmp_params, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
+        CK(dev_malloc(&tmp_params, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
         cudaError_t e = cudaMemcpyAsync(tmp_params, params_any, (size_t)pb.n_chains * HW * 3 * sizeof(double), cudaMemcpyDefault, c->stream);
-        if (e != cudaSuccess) { cudaFree(tmp_params); return fail(D3D_ECUDA, "params copy failed: %s", cudaGetErrorString(e)); }
+        if (e != cudaSuccess) { dev_free(tmp_params); return fail(D3D_ECUDA, "params copy failed: %s", cudaGetErrorString(e)); }
         d_params = tmp_params;
     }
     double* d_sim = nullptr; double* d_chi = nullptr;
     int rc = 0;
-    if (sim_out) { cudaError_t e = cudaMalloc(&d_sim, sim_cnt * sizeof(double)); if (e != cudaSuccess) rc = fail(D3D_ENOMEM, "cudaMalloc sim failed"); }
+    if (sim_out) { cudaError_t e = dev_malloc(&d_sim, sim_cnt * sizeof(double)); if (e != cudaSuccess) rc = fail(D3D_ENOMEM, "cudaMalloc sim failed"); }
     if (!rc && chi2_out) {
-        cudaError_t e = cudaMalloc(&d_chi, pb.n_chains * sizeof(double));
+        cudaError_t e = dev_malloc(&d_chi, pb.n_chains * sizeof(double));
         if (e != cudaSuccess) rc = fail(D3D_ENOMEM, "cudaMalloc chi2 failed");
         else cudaMemsetAsync(d_chi, 0, pb.n_chains * sizeof(double), c->stream);
     }
@@ -676,9 +677,9 @@ static int forward_common(d3d_ctx* c, const double* params_any, int convolve, do
     }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (!rc && e != cudaSuccess) rc = fail(D3D_ECUDA, "forward failed: %s", cudaGetErrorString(e));
-    if (tmp_params) cudaFree(tmp_params);
-    if (d_sim) cudaFree(d_sim);
-    if (d_chi) cudaFree(d_chi);
+    if (tmp_params) dev_free(tmp_params);
+    if (d_sim) dev_free(d_sim);
+    if (d_chi) dev_free(d_chi);
     return rc;
 }
 
@@ -708,15 +709,15 @@ extern "C" int d3d_simulate_clean(d3d_ctx* c, const double* params, int n_sets, 
     const size_t HW = (size_t)pb.H * pb.W;
     size_t total = (size_t)pb.n_chains * pb.D * HW;
     double *d_p = nullptr, *d_o = nullptr;
-    CK(cudaMalloc(&d_p, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
-    cudaError_t e = cudaMalloc(&d_o, total * sizeof(double));
-    if (e != cudaSuccess) { cudaFree(d_p); return fail(D3D_ENOMEM, "cudaMalloc failed"); }
+    CK(dev_malloc(&d_p, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
+    cudaError_t e = dev_malloc(&d_o, total * sizeof(double));
+    if (e != cudaSuccess) { dev_free(d_p); return fail(D3D_ENOMEM, "cudaMalloc failed"); }
     cudaMemcpyAsync(d_p, params, (size_t)pb.n_chains * HW * 3 * sizeof(double), cudaMemcpyDefault, c->stream);
     clean_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(pb, d_p, d_o);
     c->launches++;
     cudaMemcpyAsync(sim_out, d_o, total * sizeof(double), cudaMemcpyDefault, c->stream);
     e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_p); cudaFree(d_o);
+    dev_free(d_p); dev_free(d_o);
     if (e != cudaSuccess) return fail(D3D_ECUDA, "simulate_clean failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -728,7 +729,7 @@ extern "C" int d3d_get_residual(d3d_ctx* c, double* err_out) {
     const Problem& pb = c->pb;
     size_t total = (size_t)pb.n_chains * pb.D * pb.H * pb.W;
     double* d_o = nullptr;
-    CK(cudaMalloc(&d_o, total * sizeof(double)));
+    CK(dev_malloc(&d_o, total * sizeof(double)));
     long long blocks = (long long)pb.n_chains * pb.H * ((pb.Dp + 31) / 32) * ((pb.W + 31) / 32);
     if (c->dtype == D3D_F64)
         egest_kernel<double><<<(unsigned)blocks, 256, 0, c->stream>>>((const double*)pb.err, d_o, pb.n_chains, pb.D, pb.Dp, pb.H, pb.W);
@@ -737,7 +738,7 @@ extern "C" int d3d_get_residual(d3d_ctx* c, double* err_out) {
     c->launches++;
     cudaMemcpyAsync(err_out, d_o, total * sizeof(double), cudaMemcpyDefault, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_o);
+    dev_free(d_o);
     if (e != cudaSuccess) return fail(D3D_ECUDA, "get_residual failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -758,9 +759,9 @@ extern "C" int d3d_conv1d(d3d_ctx* c, const double* lines, int n, int batch, con
     }
     double *d_l = nullptr, *d_k = nullptr, *d_o = nullptr;
     size_t cnt = (size_t)n * batch;
-    CK(cudaMalloc(&d_l, cnt * sizeof(double)));
-    CK(cudaMalloc(&d_o, cnt * sizeof(double)));
-    CK(cudaMalloc(&d_k, P * sizeof(double)));
+    CK(dev_malloc(&d_l, cnt * sizeof(double)));
+    CK(dev_malloc(&d_o, cnt * sizeof(double)));
+    CK(dev_malloc(&d_k, P * sizeof(double)));
     cudaMemcpyAsync(d_l, lines, cnt * sizeof(double), cudaMemcpyDefault, c->stream);
     cudaMemcpyAsync(d_k, hk.data(), P * sizeof(double), cudaMemcpyHostToDevice, c->stream);
     size_t smem = ((size_t)P + n) * sizeof(double);
@@ -774,7 +775,7 @@ extern "C" int d3d_conv1d(d3d_ctx* c, const double* lines, int n, int batch, con
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(D3D_ECUDA, "d3d_conv1d failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_l); cudaFree(d_o); cudaFree(d_k);
+    dev_free(d_l); dev_free(d_o); dev_free(d_k);
     return rc;
 }
 
@@ -786,8 +787,8 @@ extern "C" int d3d_rtnorm(d3d_ctx* c, int n, const double* a, const double* b, c
     if (n < 1 || !a || !b || !mu || !sigma || !out) return fail(D3D_EINVAL, "d3d_rtnorm: bad argument");
     CK(cudaSetDevice(c->device));
     double* d = nullptr; int* d_used = nullptr; int* d_status = nullptr;
-    CK(cudaMalloc(&d, (size_t)n * 5 * sizeof(double)));
-    CK(cudaMalloc(&d_used, (size_t)(n + 1) * sizeof(int)));
+    CK(dev_malloc(&d, (size_t)n * 5 * sizeof(double)));
+    CK(dev_malloc(&d_used, (size_t)(n + 1) * sizeof(int)));
     d_status = d_used + n;
     cudaMemsetAsync(d_status, 0, sizeof(int), c->stream);
     const double* src[4] = {a, b, mu, sigma};
@@ -802,7 +803,7 @@ extern "C" int d3d_rtnorm(d3d_ctx* c, int n, const double* a, const double* b, c
     if (used_out) cudaMemcpyAsync(used_out, d_used, (size_t)n * sizeof(int), cudaMemcpyDefault, c->stream);
     cudaMemcpyAsync(&h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(d); cudaFree(d_used);
+    dev_free(d); dev_free(d_used);
     if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_rtnorm failed: %s", cudaGetErrorString(e));
     if (h_status) return fail(D3D_ENUMERIC, "Truncated ndst in [a,b]: b MUST be greater than a (or NaN bounds)");
     return 0;
@@ -818,7 +819,7 @@ extern "C" int d3d_delta_logl(d3d_ctx* c, int chain, int y, int x, const double 
         return fail(D3D_EINVAL, "d3d_delta_logl: bad argument");
     CK(cudaSetDevice(c->device));
     double* d_out = nullptr;
-    CK(cudaMalloc(&d_out, 3 * sizeof(double)));
+    CK(dev_malloc(&d_out, 3 * sizeof(double)));
     EvalReq ev;
     ev.enabled = 1; ev.p_new[0] = p_new[0]; ev.p_new[1] = p_new[1]; ev.p_new[2] = p_new[2];
     ev.out = d_out;
@@ -836,7 +837,7 @@ extern "C" int d3d_delta_logl(d3d_ctx* c, int chain, int y, int x, const double 
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, 3 * sizeof(double), cudaMemcpyDefault, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_out);
+    dev_free(d_out);
     if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_delta_logl failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -885,9 +886,9 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             }
             std::vector<long long> prog(C, it0);
             if (c->sched_cap < flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long)) {
-                if (c->d_sched) cudaFree(c->d_sched);
+                if (c->d_sched) dev_free(c->d_sched);
                 c->sched_cap = 2 * (flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long));
-                if (cudaMalloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; return cudaErrorMemoryAllocation; }
+                if (dev_malloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; return cudaErrorMemoryAllocation; }
             }
             char* base = (char*)c->d_sched;
             int4* d_items = (int4*)base;
@@ -1030,13 +1031,13 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         t_host = n;
     };
     if (chain_out && rows_local > 0) {
-        if (cudaMalloc(&chain_dev, (size_t)pb.n_chains * rows_local * HW * 3 * sizeof(double)) != cudaSuccess)
+        if (dev_malloc(&chain_dev, (size_t)pb.n_chains * rows_local * HW * 3 * sizeof(double)) != cudaSuccess)
             return fail(D3D_ENOMEM, "Not enough device memory for that many iterations. Use a higher value in the keep_one_in= parameter.");
         cudaMemsetAsync(chain_dev, 0, (size_t)pb.n_chains * rows_local * HW * 3 * sizeof(double), c->stream);
     }
     if (lik_out && rows_local > 0) {
-        if (cudaMalloc(&lik_dev, (size_t)pb.n_chains * rows_local * HW * sizeof(double)) != cudaSuccess) {
-            if (chain_dev) cudaFree(chain_dev);
+        if (dev_malloc(&lik_dev, (size_t)pb.n_chains * rows_local * HW * sizeof(double)) != cudaSuccess) {
+            if (chain_dev) dev_free(chain_dev);
             return fail(D3D_ENOMEM, "Not enough device memory for the likelihood chain.");
         }
         cudaMemsetAsync(lik_dev, 0, (size_t)pb.n_chains * rows_local * HW * sizeof(double), c->stream);
@@ -1120,8 +1121,8 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
     stamp("row copies enqueued");
     e = cudaStreamSynchronize(c->stream);
     stamp("row copies done");
-    if (chain_dev) cudaFree(chain_dev);
-    if (lik_dev) cudaFree(lik_dev);
+    if (chain_dev) dev_free(chain_dev);
+    if (lik_dev) dev_free(lik_dev);
     stamp("staging free");
     if (rc) return rc;
     if (e != cudaSuccess) return fail(D3D_ECUDA, "sweep failed: %s", cudaGetErrorString(e));
@@ -1169,10 +1170,10 @@ static bool is_device_ptr(const void* p) {
 
 static int rec_stage(d3d_ctx* c, size_t bytes) {
     if (bytes <= c->rec_stage_cap) return 0;
-    if (c->d_rec_stage) cudaFree(c->d_rec_stage);
+    if (c->d_rec_stage) dev_free(c->d_rec_stage);
     c->d_rec_stage = nullptr; c->rec_stage_cap = 0;
-    if (cudaMalloc(&c->d_rec_stage, bytes) != cudaSuccess)
-        return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) for the record staging buffer failed", bytes);
+    if (dev_malloc(&c->d_rec_stage, bytes) != cudaSuccess)
+        return fail(D3D_ENOMEM, "dev_malloc(%zu bytes) for the record staging buffer failed", bytes);
     c->rec_stage_cap = bytes;
     return 0;
 }
@@ -1309,10 +1310,10 @@ extern "C" int d3d_tile_fused_init(d3d_ctx* c, int n_tiles, int my_index, void**
     const size_t bytes = box_flag_bytes() + (size_t)2 * n_tiles * slots * REC_N * sizeof(double);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     c->ipc_opened.clear();
-    if (c->box && c->box_bytes < bytes) { (cudaFree)(c->box); c->box = nullptr; }
+    if (c->box && c->box_bytes < bytes) { cudaFree(c->box); c->box = nullptr; }
     if (!c->box) {
         // a plain driver allocation (not from the cache): its handle is exported to other processes
-        if ((cudaMalloc)(&c->box, bytes) != cudaSuccess) { c->box = nullptr; return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) for the tile box failed", bytes); }
+        if (cudaMalloc(&c->box, bytes) != cudaSuccess) { c->box = nullptr; return fail(D3D_ENOMEM, "dev_malloc(%zu bytes) for the tile box failed", bytes); }
         c->box_bytes = bytes;
     }
     CK(cudaMemsetAsync(c->box, 0, c->box_bytes, c->stream));
@@ -1472,12 +1473,12 @@ extern "C" int d3d_chain_mean(d3d_ctx* c, const double* chain, int64_t n_rows, i
     const bool in_dev = is_device_ptr(chain), out_dev = is_device_ptr(mean_out);
     double* d_in = nullptr; double* d_out = nullptr;
     if (!in_dev) {
-        if (cudaMalloc(&d_in, in_bytes) != cudaSuccess) return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) failed", in_bytes);
+        if (dev_malloc(&d_in, in_bytes) != cudaSuccess) return fail(D3D_ENOMEM, "dev_malloc(%zu bytes) failed", in_bytes);
         cudaMemcpyAsync(d_in, chain, in_bytes, cudaMemcpyHostToDevice, c->stream);
     }
-    if (!out_dev && cudaMalloc(&d_out, out_bytes) != cudaSuccess) {
-        if (d_in) cudaFree(d_in);
-        return fail(D3D_ENOMEM, "cudaMalloc(%zu bytes) failed", out_bytes);
+    if (!out_dev && dev_malloc(&d_out, out_bytes) != cudaSuccess) {
+        if (d_in) dev_free(d_in);
+        return fail(D3D_ENOMEM, "dev_malloc(%zu bytes) failed", out_bytes);
     }
     const long long n = (long long)pb.n_chains * row_elems;
     chain_mean_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(in_dev ? chain : d_in, pb.n_chains, n_rows,
@@ -1486,8 +1487,8 @@ extern "C" int d3d_chain_mean(d3d_ctx* c, const double* chain, int64_t n_rows, i
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && !out_dev) e = cudaMemcpyAsync(mean_out, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    if (d_in) cudaFree(d_in);
-    if (d_out) cudaFree(d_out);
+    if (d_in) dev_free(d_in);
+    if (d_out) dev_free(d_out);
     if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_chain_mean failed: %s", cudaGetErrorString(e));
     return 0;
 }
