@@ -516,7 +516,10 @@ apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ Til
     const int src = (int)(ridx / tb.slots);
     if (src == tb.my_tile) return;                           // (whole cluster)
     __shared__ int s_ok;
-    if (threadIdx.x == 0) s_ok = tile_wait_flag(tb, src, phase) ? 1 : 0;
+    // (after one time-out every later applier gives up at once: a dead peer costs seconds, not
+    // seconds per phase)
+    if (threadIdx.x == 0)
+        s_ok = (*(volatile int*)pb.status != 2 && tile_wait_flag(tb, src, phase)) ? 1 : 0;
     __syncthreads();
     if (!s_ok) { if (threadIdx.x == 0) atomicExch(pb.status, 2); return; }   // (flag state is the same for the cluster... see below)
     const double* rp = tb.inbox[tb.my_tile] + tile_inbox_index(tb, (int)(phase & 1ull), src, ridx - (long long)src * tb.slots);

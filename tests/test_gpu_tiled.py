@@ -119,6 +119,26 @@ def test_fused_peer_memory_exchange_equals_one_context(nat, case):
         np.testing.assert_allclose(r, res1, rtol=0, atol=1e-9)
 
 
+def test_fused_exchange_gives_up_on_a_silent_peer(nat):
+    """A peer that never publishes its phase must not hang the GPU: the applier's wait is bounded
+    (~2 s), later phases give up at once, and the error surfaces through the C ABI."""
+    import time
+    prob = _problem(8, 12, 14, (5, 5), 2)
+    data, var, fsf, lsf, mask, init = prob
+    ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, mask=mask, seed=3)
+    ctx.set_params(init[None])
+    ctx.forward(write_err=True)
+    ctx.set_tile(0, 12, 0, 7)
+    box = ctx.fused_init(2, 0)
+    ctx.fused_connect(1, box=box)              # "tile 1" never runs: nobody raises its flag
+    t0 = time.perf_counter()
+    ctx.sweep_fused(1, 2)                      # 50 phases, every applier waits on tile 1
+    with pytest.raises(nat.NativeError) as err:
+        ctx.chain_control()
+    assert 'timed out' in str(err.value)
+    assert time.perf_counter() - t0 < 30.0
+
+
 def test_tiling_float32_storage_and_refresh(nat):
     prob = _problem(12, 20, 22, (7, 7), 8)
     chain1, lik1, acc1, res1 = _single(nat, prob, 1, 3, dtype=nat.F32)
