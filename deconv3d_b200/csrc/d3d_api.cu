@@ -597,12 +597,13 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
         c->launches++;
         CK(cudaGetLastError());
     }
-    // register-tiled kernel for the common FSF widths (Dp is even: z-pairs), else the scalar one
+    // register-tiled kernel with compile-time width up to 17 columns (Dp is even: z-pairs), the
+    // chunked wide kernel above that (faster from 21 columns on), the scalar one as last resort
     {
         const int TYt = 8, TXt = 16, ZCt = 16;
         size_t smem_t = ((size_t)((pb.fh * pb.fw + 1) & ~1) +
                          (size_t)(TYt + pb.fh - 1) * (TXt + pb.fw - 1) * ZCt) * sizeof(double);
-        bool ok = smem_t <= 200 * 1024 && !getenv("D3D_STENCIL_SCALAR") && pb.Dp % 2 == 0;
+        bool ok = smem_t <= 200 * 1024 && !getenv("D3D_STENCIL_SCALAR") && !getenv("D3D_STENCIL_WIDE") && pb.Dp % 2 == 0;
         dim3 grid_t((unsigned)(pb.n_chains * ((pb.H + TYt - 1) / TYt) * ((pb.W + TXt - 1) / TXt)),
                     (unsigned)((pb.Dp + ZCt - 1) / ZCt));
         bool launched = false;
@@ -618,9 +619,25 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
             launched = true;                                                                        \
         }
         D3D_TILED(3) D3D_TILED(5) D3D_TILED(7) D3D_TILED(9) D3D_TILED(11) D3D_TILED(13)
-        D3D_TILED(15) D3D_TILED(17) D3D_TILED(21)
+        D3D_TILED(15) D3D_TILED(17)
 #undef D3D_TILED
         if (launched) {
+            c->launches++;
+            CK(cudaGetLastError());
+            return 0;
+        }
+        // any other width: chunked register tiling (tile 16 x 32 spaxels x 4 channels)
+        const size_t smem_w = ((size_t)((pb.fh * pb.fw + 1) & ~1) +
+                               (size_t)(16 + pb.fh - 1) * wide_row_positions(pb.fw) * 4) * sizeof(double);
+        if (smem_w <= 220 * 1024 && !getenv("D3D_STENCIL_SCALAR") && pb.Dp % 2 == 0) {
+            dim3 grid_w((unsigned)(pb.n_chains * ((pb.H + 15) / 16) * ((pb.W + 31) / 32)), (unsigned)((pb.Dp + 3) / 4));
+            if (c->dtype == D3D_F64) {
+                CK(cudaFuncSetAttribute(stencil_wide_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+                stencil_wide_kernel<double><<<grid_w, 256, smem_w, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev);
+            } else {
+                CK(cudaFuncSetAttribute(stencil_wide_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+                stencil_wide_kernel<float><<<grid_w, 256, smem_w, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev);
+            }
             c->launches++;
             CK(cudaGetLastError());
             return 0;

@@ -111,4 +111,115 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
     }
 }
 
+// ---------------------------------------------------------------------------
+// Any FSF width (e.g. 23, 31, 41 columns): the same register tiling with the FSF row walked in
+// chunks of KC = 8 taps, so that the per-thread window stays at KC + RX - 1 vectors whatever
+// the width.  CTA = 256 threads = 2 z-pairs x 8 x-blocks x 16 rows (tile 16 x 32 spaxels x 4
+// channels: the halo tile of a 41 x 41 FSF is 56 x 72 x 4 doubles = 129 KB).  The tile row
+// stride is padded to 1 (mod 4) positions: the 8 lanes of a quarter warp (2 z-pairs x 4 rows)
+// then hit 8 different 16-byte slots of a 128-byte bank line -- conflict-free LDS.128.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int wide_row_positions(int fw) {
+    int hx = 32 + fw - 1;
+    while ((hx & 3) != 1) ++hx;
+    return hx;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 1)
+stencil_wide_kernel(const __grid_constant__ Problem pb, const double* __restrict__ lines,
+                    double* sim_out, int write_err, double* chi2_out) {
+    const int TY = 16, TX = 32, RX = 4, ZC = 4, KC = 8;
+    extern __shared__ double smem_raw[];
+    const int fh = pb.fh, fw = pb.fw, Dp = pb.Dp, D = pb.D, H = pb.H, W = pb.W;
+    const int hx = TX + fw - 1, hy = TY + fh - 1, hxp = wide_row_positions(fw);
+    double* F = smem_raw;                                   // [fh][fw]
+    double* tile = F + ((fh * fw + 1) & ~1);                // [hy][hxp][ZC], 16-byte aligned
+    const int ty_n = (H + TY - 1) / TY, tx_n = (W + TX - 1) / TX;
+    const int chain = blockIdx.x / (ty_n * tx_n);
+    const int trem = blockIdx.x - chain * ty_n * tx_n;
+    const int ty0 = (trem / tx_n) * TY, tx0 = (trem % tx_n) * TX;
+    const int z0 = blockIdx.y * ZC;
+    const int cube = chain / pb.chains_per_cube;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < fh * fw; i += 256) F[i] = pb.fsf[i];
+    const double* lc = lines + (size_t)chain * H * W * Dp;
+    for (int i = tid; i < hy * hx * (ZC / 2); i += 256) {    // double2 granularity
+        const int zq = i & 1, s = i >> 1;
+        const int sy = s / hx, sx = s - sy * hx;
+        const int gy = ty0 + sy - pb.fhh, gx = tx0 + sx - pb.fhw;
+        const int z = z0 + 2 * zq;
+        double2 v = make_double2(0.0, 0.0);
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W && z < Dp)
+            v = *(const double2*)(lc + ((size_t)gy * W + gx) * Dp + z);
+        *(double2*)(tile + ((size_t)sy * hxp + sx) * ZC + 2 * zq) = v;
+    }
+    __syncthreads();
+
+    const int zq = tid & 1, oy = ((tid >> 6) << 2) | ((tid >> 1) & 3), xb = (tid >> 3) & 7;
+    double acc[RX][2];
+#pragma unroll
+    for (int r = 0; r < RX; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
+    for (int j = 0; j < fh; ++j) {
+        const double* trow = tile + ((size_t)(oy + fh - 1 - j) * hxp + xb * RX) * ZC + 2 * zq;
+        const double* frow = F + j * fw;
+        for (int k0 = 0; k0 < fw; k0 += KC) {
+            // taps k0 .. k0+KC-1 (those >= fw count as zero); output r, tap k reads window
+            // position r + fw-1-k = base + (r + KC-1 - (k - k0)) with base = fw - k0 - KC
+            const int base = fw - k0 - KC;
+            double2 v[KC + RX - 1];
+#pragma unroll
+            for (int u = 0; u < KC + RX - 1; ++u)
+                v[u] = base + u >= 0 ? *(const double2*)(trow + (size_t)(base + u) * ZC) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                const double f = k0 + kk < fw ? frow[k0 + kk] : 0.0;
+#pragma unroll
+                for (int r = 0; r < RX; ++r) {
+                    acc[r][0] = fma(f, v[r + KC - 1 - kk].x, acc[r][0]);
+                    acc[r][1] = fma(f, v[r + KC - 1 - kk].y, acc[r][1]);
+                }
+            }
+        }
+    }
+
+    const int gy = ty0 + oy;
+    const int z = z0 + 2 * zq;
+    double chi = 0.0;
+    if (gy < H && z < Dp) {
+        const T* data = (const T*)pb.data + (size_t)cube * H * W * Dp;
+        const T* ivc = pb.var_is_cube ? (const T*)pb.iv + (size_t)cube * H * W * Dp : nullptr;
+        const double ivs = pb.var_is_cube ? 0.0 : pb.iv_scalar[cube];
+        T* err = (T*)pb.err + (size_t)chain * H * W * Dp;
+        typedef typename Pair<T>::P P2;
+#pragma unroll
+        for (int r = 0; r < RX; ++r) {
+            const int gx = tx0 + xb * RX + r;
+            if (gx >= W) continue;
+            const size_t off = ((size_t)gy * W + gx) * Dp + z;
+            if (sim_out) {
+                if (z < D) sim_out[(size_t)chain * D * H * W + ((size_t)z * H + gy) * W + gx] = acc[r][0];
+                if (z + 1 < D) sim_out[(size_t)chain * D * H * W + ((size_t)(z + 1) * H + gy) * W + gx] = acc[r][1];
+            }
+            if (write_err || chi2_out) {
+                const P2 d = *(const P2*)(data + off);
+                double e0 = z < D ? (double)d.x - acc[r][0] : 0.0;
+                double e1 = z + 1 < D ? (double)d.y - acc[r][1] : 0.0;
+                if (write_err) { P2 o; o.x = (T)e0; o.y = (T)e1; *(P2*)(err + off) = o; }
+                if (chi2_out) {
+                    double w0 = ivs, w1 = ivs;
+                    if (ivc) { const P2 w = *(const P2*)(ivc + off); w0 = (double)w.x; w1 = (double)w.y; }
+                    chi = fma(e0 * e0, w0, chi);
+                    chi = fma(e1 * e1, w1, chi);
+                }
+            }
+        }
+    }
+    if (chi2_out) {
+        chi = warp_sum(chi);
+        if ((tid & 31) == 0) atomicAdd(chi2_out + chain, 0.5 * chi);
+    }
+}
+
 }  // namespace d3d

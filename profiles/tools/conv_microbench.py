@@ -44,7 +44,8 @@ def run(n, D, H, W, fs, lsf_sigma_px):
     byts = vox * 8 * 4                       # lines written + read, data read, residual written
     print('| %2dx%-2d | %.1f | %7.3f | %6.2f | %6.0f | %s |' % (
         fs, fs, lsf_sigma_px, ms, flop / ms / 1e9, byts / ms / 1e6,
-        'tiled' if fs in (3, 5, 7, 9, 11, 13, 15, 17, 21) else 'scalar z-chunk'))
+        'wide (chunked)' if os.environ.get('D3D_STENCIL_WIDE') or fs not in (3, 5, 7, 9, 11, 13, 15, 17)
+        else 'tiled<FW>'))
     ctx.close()
 
 

@@ -138,6 +138,9 @@ def test_forward_mat_known_answer(nat, dtype_name, rtol):
     ((40, 16, 14), 'ell9', 0.0002675),
     ((21, 8, 15), 'rect5x9', None),            # no LSF (lib/run.py:675-676), non-square FSF
     ((64, 6, 7), 'gauss13', 0.0006),
+    ((10, 37, 45), 'moffat23', 0.0002675),     # widths without a dedicated instantiation: the
+    ((6, 20, 70), 'rect31x41', 0.0002675),     # chunked wide stencil (partial last chunk, 2 tiles)
+    ((7, 18, 19), 'rect9x19', None),
 ])
 def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
     port, _, _ = _oracle()
@@ -149,6 +152,9 @@ def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
         'moffat7': lambda: port.moffat_fsf_image((7, 7), step, fwhm_arcsec=0.8, beta=2.5),
         'ell9': lambda: port.gaussian_fsf_image(0.6, step, pa=30., ba=0.7),
         'rect5x9': lambda: (lambda f: f / f.sum())(rs.rand(5, 9)),
+        'moffat23': lambda: port.moffat_fsf_image((23, 23), step, fwhm_arcsec=1.2, beta=2.5),
+        'rect31x41': lambda: (lambda f: f / f.sum())(rs.rand(31, 41)),
+        'rect9x19': lambda: (lambda f: f / f.sum())(rs.rand(9, 19)),
     }[fsf_kind]()
     lsf = None if lsf_fwhm is None else port.gaussian_lsf_vector(lsf_fwhm, 1.25e-4, D)
     data = synthetic(D, H, W, 3)
