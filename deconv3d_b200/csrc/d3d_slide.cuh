@@ -502,50 +502,28 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     PH_ADD(10);                                  // [10] A draws
                 }
                 // ---- unit line profile Lu = lsf (*) exp(-(z-c)^2 / (2 w^2)) -------------
-                // two channels per lane (z, z+32): the two exp() chains and, below, four
-                // independent tap accumulations overlap; taps unrolled by 4 so that their
-                // shared-memory loads are in flight together
                 {
                     const double inv2w2 = 1.0 / (2.0 * (w_prof * w_prof));
                     const int D = pb.D, P = pb.P;
-                    for (int z = lane; z < Dp; z += 64) {
-                        const int z1 = z + 32;
-                        const double d0 = (double)z - c_prof, d1 = (double)z1 - c_prof;
-                        const double g0 = exp(-1.0 * (d0 * d0) * inv2w2);
-                        const double g1 = exp(-1.0 * (d1 * d1) * inv2w2);
-                        if (z < D) g_buf[z] = g0;
-                        if (z1 < D) g_buf[z1] = g1;
+#pragma unroll 1
+                    for (int z = lane; z < D; z += 32) {
+                        const double d0 = (double)z - c_prof;
+                        g_buf[z] = exp(-1.0 * (d0 * d0) * inv2w2);
                     }
                     __syncwarp();
                     if (pb.has_lsf) {
                         const int nt = pb.ntaps;
-                        for (int z = lane; z < Dp; z += 64) {
-                            const int z1 = z + 32;
-                            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 1
+                        for (int z = lane; z < Dp; z += 32) {
+                            double a0 = 0.0, a1 = 0.0;
                             int tq = 0;
 #pragma unroll 1
-                            for (; tq + 3 < nt; tq += 4) {
-                                const int m0 = sm.Km[tq], m1 = sm.Km[tq + 1], m2 = sm.Km[tq + 2],
-                                          m3 = sm.Km[tq + 3];
-                                const double k0 = sm.Kv[tq], k1 = sm.Kv[tq + 1], k2 = sm.Kv[tq + 2],
-                                             k3 = sm.Kv[tq + 3];
-                                const double p0 = g_buf[(z - m0) & (P - 1)], p1 = g_buf[(z - m1) & (P - 1)];
-                                const double p2 = g_buf[(z - m2) & (P - 1)], p3 = g_buf[(z - m3) & (P - 1)];
-                                const double q0 = g_buf[(z1 - m0) & (P - 1)], q1 = g_buf[(z1 - m1) & (P - 1)];
-                                const double q2 = g_buf[(z1 - m2) & (P - 1)], q3 = g_buf[(z1 - m3) & (P - 1)];
-                                a0 = fma(k0, p0, a0); a1 = fma(k1, p1, a1);
-                                a0 = fma(k2, p2, a0); a1 = fma(k3, p3, a1);
-                                b0 = fma(k0, q0, b0); b1 = fma(k1, q1, b1);
-                                b0 = fma(k2, q2, b0); b1 = fma(k3, q3, b1);
+                            for (; tq + 1 < nt; tq += 2) {
+                                a0 = fma(sm.Kv[tq], g_buf[(z - sm.Km[tq]) & (P - 1)], a0);
+                                a1 = fma(sm.Kv[tq + 1], g_buf[(z - sm.Km[tq + 1]) & (P - 1)], a1);
                             }
-                            for (; tq < nt; ++tq) {
-                                const int m0 = sm.Km[tq];
-                                const double k0 = sm.Kv[tq];
-                                a0 = fma(k0, g_buf[(z - m0) & (P - 1)], a0);
-                                b0 = fma(k0, g_buf[(z1 - m0) & (P - 1)], b0);
-                            }
+                            if (tq < nt) a0 = fma(sm.Kv[tq], g_buf[(z - sm.Km[tq]) & (P - 1)], a0);
                             Lu_out[z] = z < D ? a0 + a1 : 0.0;
-                            if (z1 < Dp) Lu_out[z1] = z1 < D ? b0 + b1 : 0.0;
                         }
                     } else {                                     // lib/run.py:675-676
                         for (int z = lane; z < Dp; z += 32) Lu_out[z] = z < D ? g_buf[z] : 0.0;
