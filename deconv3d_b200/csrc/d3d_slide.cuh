@@ -209,7 +209,25 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                 int m = (grp - xl) % ngrp;
                 if (m < 0) m += ngrp;
                 const int Xn = xl + m;                           // column of this group
-                if (wt && (Xn != heldX || y != heldY)) {
+                if (wt && Xn != heldX && y == heldY && fh == NE && y >= fhh && y + fhh < H &&
+                    heldX >= 0 && heldX < W && Xn >= 0 && Xn < W) {
+                    // interior site, same row: all NE rows exist -- straight-line write-back and
+                    // reload without per-row tests (this block delays the two warps that hold
+                    // the switching group, profiles/r01_notes.md)
+                    const size_t rowoff = (size_t)(y - fhh) * W;
+                    T* p = errT + (rowoff + heldX) * Dp + zp * VEC;
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) { *(V*)p = ecache[i]; p += rstride; }
+                    const T* pe = errT + (rowoff + Xn) * Dp + zp * VEC;
+#pragma unroll
+                    for (int i = 0; i < NE; ++i) { ecache[i] = *(const V*)pe; pe += rstride; }
+                    if (IVCUBE) {
+                        const T* q = ivT + (rowoff + Xn) * Dp + zp * VEC;
+#pragma unroll
+                        for (int i = 0; i < NE; ++i) { ivcache[i] = *(const V*)q; q += rstride; }
+                    }
+                    heldX = Xn;
+                } else if (wt && (Xn != heldX || y != heldY)) {
                     const int ytop_old = heldY - fhh;
                     if (heldX >= 0 && heldX < W && heldY != NOCOL) {       // write back
                         T* p = errT + ((size_t)max(ytop_old, 0) * W + heldX) * Dp + zp * VEC;
