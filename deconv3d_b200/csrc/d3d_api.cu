@@ -283,7 +283,8 @@ static void choose_launch(d3d_ctx* c) {
         const int nwt_slide = (pb.fw + 1) * zl;
         c->slide_threads = ((nwt_slide + 31) / 32) * 32 + 96;
         c->slide_smem = c->sweep_smem_base(pb) + 2 * 4002 * sizeof(double) + 8964 * sizeof(unsigned short);
-        c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384;
+        c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384 && pb.W >= 2 &&
+                       (long long)pb.H * pb.W * pb.W < 0xffffffffLL;   // multiply-high site decode
         if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);

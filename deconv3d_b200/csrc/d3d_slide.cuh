@@ -140,6 +140,8 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
     const bool wt = tid < nwt;
 
     const int ns = pb.n_sites[cube];
+    // (the host sends one-column fields to the row-mapped kernel: W >= 2 here, the magic fits)
+    const unsigned magicW = (unsigned)((0x100000000ull + (unsigned)W - 1u) / (unsigned)W);
     const int* sites = pb.sites + (size_t)cube * pb.max_sites;
     const size_t HW = (size_t)H * W;
     const size_t row_bytes = (size_t)W * Dp * sizeof(T);
@@ -195,7 +197,10 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
         for (int j = 0; j < ns; ++j) {
             const int par = j & 1;
             const int site = sites[j];
-            const int y = site / W, x = site - y * W;
+            // y = site / W by a multiply-high with ceil(2^32 / W) (exact while site * W < 2^32,
+            // i.e. for every field the host accepts; the fix-up covers the rest)
+            int y = (int)__umulhi((unsigned)site, magicW), x = site - y * W;
+            if (x < 0) { --y; x += W; }
             double* Lu_o = sm.Lu_o + par * Dp;
             double* Lu_n = sm.Lu_n + par * Dp;
             double* prop_s = sm.prop + par * 8;
@@ -206,7 +211,8 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                 TRW(0);
                 // ---- make the resident columns current for (y, x) --------------------
                 const int xl = x - pb.fhw;
-                int m = (grp - xl) % ngrp;
+                // (square FSF of the template's size: modulo by a compile-time constant)
+                int m = fw == NE ? (grp - xl) % (NE + 1) : (grp - xl) % ngrp;
                 if (m < 0) m += ngrp;
                 const int Xn = xl + m;                           // column of this group
                 if (wt && Xn != heldX && y == heldY && fh == NE && y >= fhh && y + fhh < H &&
