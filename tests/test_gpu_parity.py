@@ -333,7 +333,7 @@ def test_coloured_mode_vs_oracle_same_order(nat):
 @pytest.mark.parametrize('fsf_shape', [(13, 13), (23, 23)])
 def test_coloured_chain_per_cta_equals_launch_per_class(nat, monkeypatch, fsf_shape):
     """Coloured mode has two schedules: one launch per colour class (few chains) and one CTA per
-    chain walking the sites in colour-class order (many chains).  Same chains, bit for bit."""
+    chain walking the sites in colour-class order (many chains).  Same decisions, same chains."""
     port, _, _ = _oracle()
     rs = np.random.RandomState(12)
     D, H, W = 12, 18, 20
@@ -354,10 +354,14 @@ def test_coloured_chain_per_cta_equals_launch_per_class(nat, monkeypatch, fsf_sh
                                 chain_out=chain, lik_out=lik)
         out.append((chain, lik, acc, its, ctx.get_residual()))
     m = mask == 1
-    assert np.array_equal(out[0][0][:, 1:][:, :, m], out[1][0][:, 1:][:, :, m])
-    assert np.array_equal(out[0][1][:, 1:][:, :, m], out[1][1][:, 1:][:, :, m])
+    # same decisions and the same chains; the two schedules use different kernels (launch per
+    # class: row-mapped / generic; chain per CTA: sliding-window kernel), i.e. different
+    # summation orders, hence a rounding-level tolerance instead of bit equality
     assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
-    assert np.array_equal(out[0][4], out[1][4])
+    scale = np.abs(out[0][0][:, :, m]).max()
+    np.testing.assert_allclose(out[0][0][:, 1:][:, :, m], out[1][0][:, 1:][:, :, m], rtol=1e-8, atol=1e-10 * scale)
+    np.testing.assert_allclose(out[0][1][:, 1:][:, :, m], out[1][1][:, 1:][:, :, m], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(out[0][4], out[1][4], rtol=0, atol=1e-8 * np.abs(data).max())
 
 
 def test_fp32_storage_chain_close(nat):
