@@ -408,6 +408,8 @@ def main():
     }
     if e2e is not None:
         line['e2e'] = e2e
+    if world == 1 and args.workload == 'cfg2x256' and args.mode == 'sequential':
+        line['cfg2_single_chain'] = single_chain_probe(args, local_rank, stream)
     if world == 1 and not args.no_cpu_baseline:
         cs = args.cpu_sweeps or 3
         n_procs = min(os.cpu_count() or 1, 8)
@@ -420,6 +422,37 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def single_chain_probe(args, local_rank, stream, sweeps=200):
+    """BASELINE.json configs[1] taken literally: ONE sequential-exact chain on the cfg2 cube (one
+    CTA on one SM, latency-bound, state resident in L2).  Reported next to the many-chain
+    headline so that both regimes of the metric are on the line; not part of the timed steps."""
+    import torch
+    from deconv3d_b200 import _native, rtnorm_tables
+    wl = build_workload('cfg2', 1)
+    arrays = realise(wl, 0)
+    ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_rtnorm_tables(*rtnorm_tables.tables())
+    ctx.set_rng(42, 0)
+    ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                    arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=1)
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+    ctx.sweep(1, 50, mode=_native.SEQ_EXACT, refresh_every=1000, min_acceptance_rate=0.0)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.sweep(51, sweeps, mode=_native.SEQ_EXACT, refresh_every=1000, min_acceptance_rate=0.0)
+    e1.record(stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    upd = ctx.counters()['last_sweep_site_updates']
+    ctx.close()
+    return {'value': upd / (ms * 1e-3), 'unit': UNIT, 'sweeps_per_s': sweeps / (ms * 1e-3),
+            'us_per_site_update': ms * 1e3 / upd, 'sweeps': sweeps, 'chains': 1,
+            'workload': wl['desc'], 'mode': 'sequential'}
 
 
 def bench_tiled(args, rank, local_rank, world, sweeps):

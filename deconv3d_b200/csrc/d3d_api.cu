@@ -594,7 +594,17 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
         unsigned blocks = (unsigned)std::min<size_t>((total + spb - 1) / spb, 148 * 32);
         size_t smem = ((size_t)pb.P + (pb.P + 1) / 2 + (size_t)spb * pb.P + (size_t)spb * 4) * sizeof(double);
         if (total >= ((size_t)1 << 31)) return fail(D3D_EINVAL, "too many spaxels for one forward call");
-        lines_kernel<<<blocks, threads, smem, c->stream>>>(pb, d_params, c->d_lines, convolve);
+        // warp-shuffle spectral pass (one warp per spaxel) whenever the padded depth fits 4 registers
+        // per lane; the shared-memory kernel for deeper cubes (and under D3D_LINES_SMEM, for A/B runs)
+        const int R = pb.P <= 32 ? 1 : pb.P <= 64 ? 2 : pb.P <= 128 ? 4 : 0;
+        const unsigned wblocks = (unsigned)std::min<size_t>((total + 7) / 8, 148 * 16);
+        if (R && pb.Dp <= 32 * R && pb.ntaps <= 32 * R && !getenv("D3D_LINES_SMEM")) {
+            if (R == 1) lines_warp_kernel<1><<<wblocks, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve);
+            else if (R == 2) lines_warp_kernel<2><<<wblocks, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve);
+            else lines_warp_kernel<4><<<wblocks, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve);
+        } else {
+            lines_kernel<<<blocks, threads, smem, c->stream>>>(pb, d_params, c->d_lines, convolve);
+        }
         c->launches++;
         CK(cudaGetLastError());
     }

@@ -1110,6 +1110,78 @@ __global__ void lines_kernel(const __grid_constant__ Problem pb, const double* p
     }
 }
 
+// Warp-shuffle form of the spectral pass (same arithmetic and summation order as
+// lines_kernel, so the two are bit-identical): one warp per spaxel, lane l keeps channels
+// l, l+32, ... of the zero-padded circular buffer (length P <= 32*R) in registers; tap m of
+// the circular LSF kernel reads channel (z - m) mod P, i.e. lane (l - m) mod 32 of slot
+// (k + ((l - m) mod P) / 32) mod R: R shuffles per tap for R outputs.  No shared-memory
+// buffer and no block barrier inside the spaxel loop; a warp stores 32 consecutive
+// channels (256 bytes) per instruction.
+template <int R>
+__global__ void __launch_bounds__(256) lines_warp_kernel(const __grid_constant__ Problem pb,
+                                                         const double* __restrict__ params,
+                                                         double* __restrict__ lines, int convolve) {
+    __shared__ double Kv[32 * R];
+    __shared__ int Km[32 * R];
+    const int D = pb.D, Dp = pb.Dp, P = pb.P, nt = pb.ntaps;
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) { Kv[i] = pb.ktap_v[i]; Km[i] = pb.ktap_m[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const unsigned HW = (unsigned)(pb.H * pb.W);
+    const unsigned total = (unsigned)pb.n_chains * HW;      // (host guarantees < 2^31)
+    const bool conv = convolve && pb.has_lsf;
+    for (unsigned sp = blockIdx.x * wpb + (threadIdx.x >> 5); sp < total; sp += gridDim.x * wpb) {
+        const unsigned chain = sp / HW, site = sp - chain * HW;
+        const bool on = pb.mask[(size_t)(chain / pb.chains_per_cube) * HW + site] == 1;
+        const double* p = params + (size_t)sp * 3;
+        const double a = p[0], c = p[1], w = p[2];
+        const double q = 1.0 / (2.0 * (w * w));
+        double g[R], v[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int z = 32 * k + lane;
+            g[k] = 0.0;
+            if (on && z < D) {
+                const double d = (double)z - c;
+                g[k] = a * exp(-1.0 * (d * d) * q);                           // lib/line_models.py:109
+            }
+        }
+        if (conv) {
+            double a0[R], a1[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) a0[k] = a1[k] = 0.0;
+            auto tap = [&](int t, double (&acc)[R]) {
+                const double kv = Kv[t];
+                const int j = (lane - Km[t]) & (P - 1);
+                const int q0 = j >> 5;
+                double s[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s[r] = __shfl_sync(0xffffffffu, g[r], j & 31);
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    double x = s[0];
+#pragma unroll
+                    for (int r = 1; r < R; ++r) x = (((k + q0) & (R - 1)) == r) ? s[r] : x;
+                    acc[k] = fma(kv, x, acc[k]);
+                }
+            };
+            int t = 0;
+            for (; t + 1 < nt; t += 2) { tap(t, a0); tap(t + 1, a1); }
+            if (t < nt) tap(t, a0);
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = a0[k] + a1[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < R; ++k) v[k] = g[k];
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            const int z = 32 * k + lane;
+            if (z < Dp) lines[(size_t)sp * Dp + z] = (on && z < D) ? v[k] : 0.0;
+        }
+    }
+}
+
 // Pass 2 (spatial): true 2-D convolution with the FSF, zero 'same' borders
 // (scipy.signal.convolve2d(..., 'same'), lib/run.py:1027-1029, equal to the paste
 // at lib/run.py:697-706).  CTA = TY x TX output spaxels x ZC channels; the

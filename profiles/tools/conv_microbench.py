@@ -50,6 +50,9 @@ def run(n, D, H, W, fs, lsf_sigma_px):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) == 3:                   # one configuration (for ncu): FSF size, LSF sigma in px
+        run(1024, 32, 32, 32, int(sys.argv[1]), float(sys.argv[2]))
+        sys.exit(0)
     print('forward model, 1024 cubes of 32x32x32, f64, one B200; B_fwd counted as 4 x 8 bytes per voxel')
     print('| FSF | LSF sigma px | ms | TFLOP/s fp64 (FSF pass) | GB/s | spatial kernel |')
     print('|---|---|---|---|---|---|')

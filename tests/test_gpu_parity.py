@@ -141,6 +141,9 @@ def test_forward_mat_known_answer(nat, dtype_name, rtol):
     ((10, 37, 45), 'moffat23', 0.0002675),     # widths without a dedicated instantiation: the
     ((6, 20, 70), 'rect31x41', 0.0002675),     # chunked wide stencil (partial last chunk, 2 tiles)
     ((7, 18, 19), 'rect9x19', None),
+    ((70, 6, 9), 'moffat7', 0.0006),           # P=128: four channels per lane in the warp-shuffle pass
+    ((128, 5, 6), 'moffat7', 0.0004),          # P=128 full wrap
+    ((130, 5, 6), 'moffat7', 0.0004),          # P=256: shared-memory spectral kernel
 ])
 def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
     port, _, _ = _oracle()
@@ -174,6 +177,31 @@ def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
     np.testing.assert_allclose(ctx.simulate_clean(params[None])[0],
                                port.simulate_clean(data.shape, params, mask),
                                rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize('D', [12, 32, 40, 64, 100])
+def test_spectral_pass_warp_shuffle_equals_shared_memory_kernel(nat, monkeypatch, D):
+    """The warp-shuffle spectral pass (lines_warp_kernel, registers + __shfl) and the
+    shared-memory one (lines_kernel) keep the same summation order: bit-identical cubes."""
+    port, _, _ = _oracle()
+    H, W = 7, 9
+    rs = np.random.RandomState(D)
+    fsf = port.moffat_fsf_image((5, 5), 0.2, fwhm_arcsec=0.8, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0005, 1.25e-4, D)
+    data = synthetic(D, H, W, 5)
+    mask = (rs.rand(H, W) > 0.2).astype(float)
+    params = np.dstack([rs.rand(H, W) * 9, rs.rand(H, W) * (D - 1), 0.3 + rs.rand(H, W) * 4])
+    out = []
+    for smem in (False, True):
+        if smem:
+            monkeypatch.setenv('D3D_LINES_SMEM', '1')
+        ctx, _, _ = make_ctx(nat, data, np.array([0.01]), fsf, lsf, mask=mask)
+        ctx.set_params(params[None])
+        sim, _ = ctx.forward(want_sim=True, write_err=True)
+        out.append((sim.copy(), ctx.get_residual().copy()))
+        ctx.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
 
 
 @pytest.mark.parametrize('var_kind', ['scalar', 'cube'])
