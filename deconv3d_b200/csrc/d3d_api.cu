@@ -136,6 +136,7 @@ struct d3d_ctx {
     std::vector<void*> allocs;          // problem-lifetime allocations
     void* rt_x = nullptr; void* rt_yu = nullptr; void* rt_nc = nullptr;
     double* d_lines = nullptr;          // [n_chains][H][W][Dp] scratch of the forward model
+    int tap_runs = 0, tap_run2 = 0;     // runs of consecutive LSF tap offsets; first tap of the second run
     int threads = 256, ne = 0;          // sweep launch configuration (row-mapped kernels)
     int generic_threads = 256;
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
@@ -438,6 +439,11 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
             if (hk[m] != 0.0 && fabs(hk[m]) >= 1e-18 * kmax) { tapv.push_back(hk[m]); tapm.push_back(m); }
     }
     pb.ntaps = (int)tapv.size();
+    // runs of consecutive tap offsets (lines_warp_kernel rotates its buffer inside a run)
+    c->tap_runs = tapm.empty() ? 0 : 1;
+    c->tap_run2 = (int)tapm.size();
+    for (size_t t = 1; t < tapm.size(); ++t)
+        if (tapm[t] != tapm[t - 1] + 1) { if (++c->tap_runs == 2) c->tap_run2 = (int)t; }
     double* d_fsf; double* d_k; double* d_tv; int* d_tm;
     if ((rc = dalloc(c, &d_fsf, hfsf.size() * sizeof(double)))) return rc;
     if ((rc = dalloc(c, &d_k, hk.size() * sizeof(double)))) return rc;
@@ -597,11 +603,13 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
         // warp-shuffle spectral pass (one warp per spaxel) whenever the padded depth fits 4 registers
         // per lane; the shared-memory kernel for deeper cubes (and under D3D_LINES_SMEM, for A/B runs)
         const int R = pb.P <= 32 ? 1 : pb.P <= 64 ? 2 : pb.P <= 128 ? 4 : 0;
-        const unsigned wblocks = (unsigned)std::min<size_t>((total + 7) / 8, 148 * 16);
-        if (R && pb.Dp <= 32 * R && pb.ntaps <= 32 * R && !getenv("D3D_LINES_SMEM")) {
-            if (R == 1) lines_warp_kernel<1><<<wblocks, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve);
-            else if (R == 2) lines_warp_kernel<2><<<wblocks, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve);
-            else lines_warp_kernel<4><<<wblocks, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve);
+        const size_t wblocks = (size_t)pb.n_chains * ((HW + LINES_SPB - 1) / LINES_SPB);
+        if (R && pb.Dp <= 32 * R && pb.ntaps <= 32 * R && c->tap_runs <= 2 && wblocks < ((size_t)1 << 31) &&
+            !getenv("D3D_LINES_SMEM")) {
+            const unsigned wb = (unsigned)wblocks;
+            if (R == 1) lines_warp_kernel<1><<<wb, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve, c->tap_run2);
+            else if (R == 2) lines_warp_kernel<2><<<wb, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve, c->tap_run2);
+            else lines_warp_kernel<4><<<wb, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve, c->tap_run2);
         } else {
             lines_kernel<<<blocks, threads, smem, c->stream>>>(pb, d_params, c->d_lines, convolve);
         }
@@ -611,26 +619,35 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
     // register-tiled kernel with compile-time width up to 17 columns (Dp is even: z-pairs), the
     // chunked wide kernel above that (faster from 21 columns on), the scalar one as last resort
     {
-        const int TYt = 8, TXt = 16, ZCt = 16;
-        size_t smem_t = ((size_t)((pb.fh * pb.fw + 1) & ~1) +
-                         (size_t)(TYt + pb.fh - 1) * (TXt + pb.fw - 1) * ZCt) * sizeof(double);
+        // two output rows per thread (tile 16 x 16) while two CTAs of that tile still fit an SM
+        const int TXt = 16, ZCt = 16;
+        auto tiled_smem = [&](int ty) {
+            return ((size_t)pb.fh * (pb.fw + 1) + (size_t)(ty + pb.fh - 1) * (TXt + pb.fw - 1) * ZCt) * sizeof(double);
+        };
+        const int RYt = (pb.H > 8 && tiled_smem(16) <= 110 * 1024 && !getenv("D3D_STENCIL_RY1")) ? 2 : 1;
+        const int TYt = 8 * RYt;
+        size_t smem_t = tiled_smem(TYt);
         bool ok = smem_t <= 200 * 1024 && !getenv("D3D_STENCIL_SCALAR") && !getenv("D3D_STENCIL_WIDE") && pb.Dp % 2 == 0;
         dim3 grid_t((unsigned)(pb.n_chains * ((pb.H + TYt - 1) / TYt) * ((pb.W + TXt - 1) / TXt)),
                     (unsigned)((pb.Dp + ZCt - 1) / ZCt));
         bool launched = false;
+#define D3D_TILED_RY(TT, FWV, RYV)                                                                  \
+        {                                                                                           \
+            CK(cudaFuncSetAttribute(stencil_tiled_kernel<TT, FWV, RYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+            stencil_tiled_kernel<TT, FWV, RYV><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev); \
+        }
 #define D3D_TILED(FWV)                                                                              \
         if (ok && !launched && pb.fw == FWV) {                                                      \
             if (c->dtype == D3D_F64) {                                                              \
-                CK(cudaFuncSetAttribute(stencil_tiled_kernel<double, FWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-                stencil_tiled_kernel<double, FWV><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev); \
+                if (RYt == 2) D3D_TILED_RY(double, FWV, 2) else D3D_TILED_RY(double, FWV, 1)        \
             } else {                                                                                \
-                CK(cudaFuncSetAttribute(stencil_tiled_kernel<float, FWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-                stencil_tiled_kernel<float, FWV><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev); \
+                if (RYt == 2) D3D_TILED_RY(float, FWV, 2) else D3D_TILED_RY(float, FWV, 1)          \
             }                                                                                       \
             launched = true;                                                                        \
         }
         D3D_TILED(3) D3D_TILED(5) D3D_TILED(7) D3D_TILED(9) D3D_TILED(11) D3D_TILED(13)
         D3D_TILED(15) D3D_TILED(17)
+#undef D3D_TILED_RY
 #undef D3D_TILED
         if (launched) {
             c->launches++;

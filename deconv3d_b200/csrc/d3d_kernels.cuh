@@ -1113,27 +1113,39 @@ __global__ void lines_kernel(const __grid_constant__ Problem pb, const double* p
 // Warp-shuffle form of the spectral pass (same arithmetic and summation order as
 // lines_kernel, so the two are bit-identical): one warp per spaxel, lane l keeps channels
 // l, l+32, ... of the zero-padded circular buffer (length P <= 32*R) in registers; tap m of
-// the circular LSF kernel reads channel (z - m) mod P, i.e. lane (l - m) mod 32 of slot
-// (k + ((l - m) mod P) / 32) mod R: R shuffles per tap for R outputs.  No shared-memory
-// buffer and no block barrier inside the spaxel loop; a warp stores 32 consecutive
-// channels (256 bytes) per instruction.
+// the circular LSF kernel reads channel (z - m) mod P.  The taps are ascending in m and form
+// at most two runs of consecutive offsets (an arc of the ring that wraps at most once), so
+// within a run the buffer is simply rotated by one channel per tap: per tap one 8-byte LDS
+// (tap value), R 64-bit shuffles with a loop-invariant source lane and R DFMA.  No
+// shared-memory buffer, no block barrier and no integer division inside the spaxel loop
+// (a CTA works on LINES_SPB consecutive spaxels of ONE chain); a warp stores 32 consecutive
+// channels (256 bytes) per instruction.  LSF vectors with gaps (more than two runs) take
+// the shared-memory kernel.
+#define LINES_SPB 32
 template <int R>
 __global__ void __launch_bounds__(256) lines_warp_kernel(const __grid_constant__ Problem pb,
                                                          const double* __restrict__ params,
-                                                         double* __restrict__ lines, int convolve) {
+                                                         double* __restrict__ lines, int convolve,
+                                                         int run2 /* first tap of the second run, or ntaps */) {
     __shared__ double Kv[32 * R];
-    __shared__ int Km[32 * R];
     const int D = pb.D, Dp = pb.Dp, P = pb.P, nt = pb.ntaps;
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) { Kv[i] = pb.ktap_v[i]; Km[i] = pb.ktap_m[i]; }
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) Kv[i] = pb.ktap_v[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const unsigned HW = (unsigned)(pb.H * pb.W);
-    const unsigned total = (unsigned)pb.n_chains * HW;      // (host guarantees < 2^31)
+    const unsigned nb = (HW + LINES_SPB - 1) / LINES_SPB;   // CTAs per chain
+    const unsigned chain = blockIdx.x / nb;
+    const unsigned site0 = (blockIdx.x - chain * nb) * LINES_SPB;
+    const uint8_t* mask = pb.mask + (size_t)(chain / pb.chains_per_cube) * HW;
     const bool conv = convolve && pb.has_lsf;
-    for (unsigned sp = blockIdx.x * wpb + (threadIdx.x >> 5); sp < total; sp += gridDim.x * wpb) {
-        const unsigned chain = sp / HW, site = sp - chain * HW;
-        const bool on = pb.mask[(size_t)(chain / pb.chains_per_cube) * HW + site] == 1;
-        const double* p = params + (size_t)sp * 3;
+    const int src1 = (lane - 1) & (P - 1) & 31;             // rotate by one channel
+    const int m0 = nt > 0 ? pb.ktap_m[0] : 0, m1 = run2 < nt ? pb.ktap_m[run2] : 0;
+    for (unsigned i = threadIdx.x >> 5; i < LINES_SPB; i += wpb) {
+        const unsigned site = site0 + i;
+        if (site >= HW) break;
+        const size_t sp = (size_t)chain * HW + site;
+        const bool on = mask[site] == 1;
+        const double* p = params + sp * 3;
         const double a = p[0], c = p[1], w = p[2];
         const double q = 1.0 / (2.0 * (w * w));
         double g[R], v[R];
@@ -1147,27 +1159,42 @@ __global__ void __launch_bounds__(256) lines_warp_kernel(const __grid_constant__
             }
         }
         if (conv) {
-            double a0[R], a1[R];
+            double a0[R], a1[R];                             // taps of even / odd index (lines_kernel)
 #pragma unroll
             for (int k = 0; k < R; ++k) a0[k] = a1[k] = 0.0;
-            auto tap = [&](int t, double (&acc)[R]) {
-                const double kv = Kv[t];
-                const int j = (lane - Km[t]) & (P - 1);
-                const int q0 = j >> 5;
-                double s[R];
+            for (int run = 0; run < 2; ++run) {
+                const int tb = run ? run2 : 0, te = run ? nt : run2;
+                if (tb >= te) continue;
+                // r[k][lane] = g[(32k + lane - m) mod P] for the first tap m of the run
+                const int j = (lane - (run ? m1 : m0)) & (P - 1);
+                double r[R];
+                {
+                    double s[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) s[r] = __shfl_sync(0xffffffffu, g[r], j & 31);
+                    for (int k = 0; k < R; ++k) s[k] = __shfl_sync(0xffffffffu, g[k], j & 31);
 #pragma unroll
-                for (int k = 0; k < R; ++k) {
-                    double x = s[0];
+                    for (int k = 0; k < R; ++k) {
+                        double x = s[0];
 #pragma unroll
-                    for (int r = 1; r < R; ++r) x = (((k + q0) & (R - 1)) == r) ? s[r] : x;
-                    acc[k] = fma(kv, x, acc[k]);
+                        for (int rr = 1; rr < R; ++rr) x = (((k + (j >> 5)) & (R - 1)) == rr) ? s[rr] : x;
+                        r[k] = x;
+                    }
                 }
-            };
-            int t = 0;
-            for (; t + 1 < nt; t += 2) { tap(t, a0); tap(t + 1, a1); }
-            if (t < nt) tap(t, a0);
+                auto tap = [&](int t, double (&acc)[R]) {
+                    const double kv = Kv[t];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) acc[k] = fma(kv, r[k], acc[k]);
+                    double s[R];
+#pragma unroll
+                    for (int k = 0; k < R; ++k) s[k] = __shfl_sync(0xffffffffu, r[k], src1);
+#pragma unroll
+                    for (int k = 0; k < R; ++k) r[k] = (R > 1 && lane == 0) ? s[(k + R - 1) % R] : s[k];
+                };
+                int t = tb;
+                if (t & 1) { tap(t, a1); ++t; }
+                for (; t + 1 < te; t += 2) { tap(t, a0); tap(t + 1, a1); }
+                if (t < te) tap(t, a0);
+            }
 #pragma unroll
             for (int k = 0; k < R; ++k) v[k] = a0[k] + a1[k];
         } else {
@@ -1177,7 +1204,7 @@ __global__ void __launch_bounds__(256) lines_warp_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < R; ++k) {
             const int z = 32 * k + lane;
-            if (z < Dp) lines[(size_t)sp * Dp + z] = (on && z < D) ? v[k] : 0.0;
+            if (z < Dp) lines[sp * Dp + z] = (on && z < D) ? v[k] : 0.0;
         }
     }
 }

@@ -19,16 +19,20 @@ template <typename T> struct Pair;
 template <> struct Pair<double> { typedef double2 P; };
 template <> struct Pair<float>  { typedef float2  P; };
 
-template <typename T, int FW>
+template <typename T, int FW, int RY>
 __global__ void __launch_bounds__(256, 2)
 stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restrict__ lines,
                      double* sim_out, int write_err, double* chi2_out) {
-    const int TY = 8, TX = 16, RX = 4, ZC = 16;
+    // RY output rows per thread (tile of 8*RY x 16 spaxels): a tile row loaded from shared memory
+    // serves RY output rows, and the FSF row is read as 16-byte pairs (row stride FW+1), so that
+    // the LDS pipe (4 cycles per LDS.128 of a warp) stays below the FP64 pipe (2 DFMA warps/cycle):
+    // RY = 1: 16 tile + 13 FSF loads per 104 DFMA (13 columns); RY = 2: 16 + 14 per 208.
+    const int TY = 8 * RY, TX = 16, RX = 4, ZC = 16, FWP = FW + 1;
     extern __shared__ double smem_raw[];
     const int fh = pb.fh, Dp = pb.Dp, D = pb.D, H = pb.H, W = pb.W;
     const int hx = TX + FW - 1, hy = TY + fh - 1;
-    double* F = smem_raw;                                   // [fh][FW]
-    double* tile = F + ((fh * FW + 1) & ~1);                // [hy][hx][ZC], 16-byte aligned
+    double* F = smem_raw;                                   // [fh][FW+1], last column 0
+    double* tile = F + fh * FWP;                            // [hy][hx][ZC], 16-byte aligned
     const int ty_n = (H + TY - 1) / TY, tx_n = (W + TX - 1) / TX;
     const int chain = blockIdx.x / (ty_n * tx_n);
     const int trem = blockIdx.x - chain * ty_n * tx_n;
@@ -37,8 +41,26 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
     const int cube = chain / pb.chains_per_cube;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < fh * FW; i += 256) F[i] = pb.fsf[i];
+    for (int i = tid; i < fh * FWP; i += 256) {
+        const int j = i / FWP, k = i - j * FWP;
+        F[i] = k < FW ? pb.fsf[j * FW + k] : 0.0;
+    }
     const double* lc = lines + (size_t)chain * H * W * Dp;
+    if (write_err || chi2_out) {
+        // the epilogue's `data` vectors: ask L2 for them now, so that the loads behind the FSF loop
+        // pay an L2 hit instead of a DRAM round trip with only 16 warps per SM to hide it
+        const T* data = (const T*)pb.data + (size_t)cube * H * W * Dp;
+        const int pz = z0 + 2 * (tid & 7), pxb = (tid >> 3) & 3, poy = tid >> 5;
+#pragma unroll
+        for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+            for (int r = 0; r < RX; ++r) {
+                const int gy = ty0 + poy * RY + ry, gx = tx0 + pxb * RX + r;
+                if (gy < H && gx < W && pz < Dp)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(data + ((size_t)gy * W + gx) * Dp + pz));
+            }
+    }
+#pragma unroll 4
     for (int i = tid; i < hy * hx * (ZC / 2); i += 256) {    // double2 granularity
         const int zq = i & 7, s = i >> 3;
         const int sy = s / hx, sx = s - sy * hx;
@@ -52,30 +74,46 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
     __syncthreads();
 
     const int zq = tid & 7, xb = (tid >> 3) & 3, oy = tid >> 5;
-    double acc[RX][2];
+    double acc[RY][RX][2];
 #pragma unroll
-    for (int r = 0; r < RX; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
-    for (int j = 0; j < fh; ++j) {
-        // tile row of (y' + fhh - j): oy + fh - 1 - j; element u of the window = sx xb*4 + u
-        const double* trow = tile + ((size_t)(oy + fh - 1 - j) * hx + xb * RX) * ZC + 2 * zq;
-        const double* frow = F + j * FW;
+    for (int ry = 0; ry < RY; ++ry)
+#pragma unroll
+        for (int r = 0; r < RX; ++r) { acc[ry][r][0] = 0.0; acc[ry][r][1] = 0.0; }
+    // tile row oy*RY + trr feeds FSF row j = ry + fh-1 - trr of output row ry; trr descending keeps
+    // the accumulation order of every output at j = 0, 1, ... (k ascending inside)
+    for (int trr = fh + RY - 2; trr >= 0; --trr) {
+        const double* trow = tile + ((size_t)(oy * RY + trr) * hx + xb * RX) * ZC + 2 * zq;
         double2 v[FW + RX - 1];
 #pragma unroll
         for (int u = 0; u < FW + RX - 1; ++u) v[u] = *(const double2*)(trow + (size_t)u * ZC);
 #pragma unroll
-        for (int k = 0; k < FW; ++k) {
-            const double f = frow[k];
+        for (int ry = 0; ry < RY; ++ry) {
+            const int j = ry + fh - 1 - trr;
+            if (j < 0 || j >= fh) continue;                  // uniform over the CTA
+            const double2* frow = (const double2*)(F + j * FWP);
 #pragma unroll
-            for (int r = 0; r < RX; ++r) {                   // output r, tap k -> u = r + FW-1-k
-                acc[r][0] = fma(f, v[r + FW - 1 - k].x, acc[r][0]);
-                acc[r][1] = fma(f, v[r + FW - 1 - k].y, acc[r][1]);
+            for (int k2 = 0; k2 < FWP / 2; ++k2) {
+                const double2 f2 = frow[k2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = 2 * k2 + h;
+                    if (k >= FW) continue;
+                    const double f = h ? f2.y : f2.x;
+#pragma unroll
+                    for (int r = 0; r < RX; ++r) {           // output r, tap k -> u = r + FW-1-k
+                        acc[ry][r][0] = fma(f, v[r + FW - 1 - k].x, acc[ry][r][0]);
+                        acc[ry][r][1] = fma(f, v[r + FW - 1 - k].y, acc[ry][r][1]);
+                    }
+                }
             }
         }
     }
 
-    const int gy = ty0 + oy;
     const int z = z0 + 2 * zq;
     double chi = 0.0;
+#pragma unroll
+    for (int ry = 0; ry < RY; ++ry) {
+    const int gy = ty0 + oy * RY + ry;
     if (gy < H && z < Dp) {
         const T* data = (const T*)pb.data + (size_t)cube * H * W * Dp;
         const T* ivc = pb.var_is_cube ? (const T*)pb.iv + (size_t)cube * H * W * Dp : nullptr;
@@ -88,13 +126,13 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
             if (gx >= W) continue;
             const size_t off = ((size_t)gy * W + gx) * Dp + z;
             if (sim_out) {
-                if (z < D) sim_out[(size_t)chain * D * H * W + ((size_t)z * H + gy) * W + gx] = acc[r][0];
-                if (z + 1 < D) sim_out[(size_t)chain * D * H * W + ((size_t)(z + 1) * H + gy) * W + gx] = acc[r][1];
+                if (z < D) sim_out[(size_t)chain * D * H * W + ((size_t)z * H + gy) * W + gx] = acc[ry][r][0];
+                if (z + 1 < D) sim_out[(size_t)chain * D * H * W + ((size_t)(z + 1) * H + gy) * W + gx] = acc[ry][r][1];
             }
             if (write_err || chi2_out) {
                 const P2 d = *(const P2*)(data + off);
-                double e0 = z < D ? (double)d.x - acc[r][0] : 0.0;
-                double e1 = z + 1 < D ? (double)d.y - acc[r][1] : 0.0;
+                double e0 = z < D ? (double)d.x - acc[ry][r][0] : 0.0;
+                double e1 = z + 1 < D ? (double)d.y - acc[ry][r][1] : 0.0;
                 if (write_err) { P2 o; o.x = (T)e0; o.y = (T)e1; *(P2*)(err + off) = o; }
                 if (chi2_out) {
                     double w0 = ivs, w1 = ivs;
@@ -104,6 +142,7 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
                 }
             }
         }
+    }
     }
     if (chi2_out) {
         chi = warp_sum(chi);
