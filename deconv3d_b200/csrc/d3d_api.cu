@@ -174,6 +174,7 @@ static void free_problem(d3d_ctx* c) {
     for (void* p : c->allocs) dev_free(p);
     c->allocs.clear();
     c->d_lines = nullptr;
+    c->pb.gtab = nullptr;
     c->have_problem = false;
     c->have_params = false;
 }
@@ -894,6 +895,14 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
                               long long rows_local) {
     if (NE != 0 && c->use_slide) {
         const int ne = NE ? NE : 7;
+        if (!c->pb.gtab) {                                      // static G table, once per problem
+            double* g = nullptr;
+            const size_t n = (size_t)c->pb.n_cubes * c->pb.H * c->pb.W;
+            if (dalloc(c, &g, n * c->pb.Dp * sizeof(double))) return cudaErrorMemoryAllocation;
+            gtable_kernel<T, IV><<<(unsigned)n, 64, 0, c->stream>>>(c->pb, g);
+            c->launches++;
+            c->pb.gtab = g;
+        }
         cudaFuncSetAttribute(sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slide_smem);
         // balance chains over the SMs (McNaughton wrap-around of the chain x sweep rectangle)

@@ -49,6 +49,7 @@ struct Problem {
     const int* sites;          // [cube][max_sites]  linear y*W+x, row-major (lib/run.py:553-566)
     const int* n_sites;        // [cube]
     const double* fsf;         // [fh*fw]
+    const double* gtab;        // [cube][H*W][Dp] sum of F^2/sigma^2 over the window of a site (d3d_slide.cuh), or NULL
     const double* kcirc;       // [P] circular LSF kernel (lib/convolution.py:89-160 in direct form)
     const double* ktap_v;      // [ntaps] values and
     const int* ktap_m;         // [ntaps] offsets m of the taps with |K[m]| >= 1e-18 max|K|

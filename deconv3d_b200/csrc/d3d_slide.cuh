@@ -89,6 +89,62 @@ __device__ __forceinline__ int warp_sum8_slot(int lane) {
     return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 }
 
+// Two per-lane partial sums -> two warp totals with 5 double shuffles: lane 0 ends with the
+// total of p0, lane 16 with the total of p1.
+__device__ __forceinline__ double warp_sum2(double p0, double p1, int lane) {
+    const bool b4 = lane & 16;
+    double w = (b4 ? p1 : p0) + __shfl_xor_sync(0xffffffffu, b4 ? p0 : p1, 16);
+    w += __shfl_xor_sync(0xffffffffu, w, 8);
+    w += __shfl_xor_sync(0xffffffffu, w, 4);
+    w += __shfl_xor_sync(0xffffffffu, w, 2);
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    return w;
+}
+// Four per-lane partial sums -> four warp totals with 6 double shuffles: every lane ends
+// with the total of slot ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1), i.e. lanes 0 / 16 / 8 / 24
+// hold q0 / q1 / q2 / q3.
+__device__ __forceinline__ double warp_sum4(const double* q, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const double w01 = (b4 ? q[1] : q[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q[0] : q[1], 16);
+    const double w23 = (b4 ? q[3] : q[2]) + __shfl_xor_sync(0xffffffffu, b4 ? q[2] : q[3], 16);
+    double w = (b3 ? w23 : w01) + __shfl_xor_sync(0xffffffffu, b3 ? w01 : w23, 8);
+    w += __shfl_xor_sync(0xffffffffu, w, 4);
+    w += __shfl_xor_sync(0xffffffffu, w, 2);
+    w += __shfl_xor_sync(0xffffffffu, w, 1);
+    return w;
+}
+
+// G[cube][site][z] = sum over the in-cube part of the FSF window of F^2 / sigma^2 (header of
+// d3d_kernels.cuh).  It depends on the FSF, the variance and the site only -- not on the residual
+// or the parameters -- so the sliding-window kernel reads it from this table (built once per
+// problem, H*W*Dp doubles per cube) instead of accumulating it at every site update: the window
+// warps are left with h[z] alone, and the four quadratic sums over G are formed by warp B from
+// the line profiles while it waits for the window warps.
+template <typename T, bool IVCUBE>
+__global__ void gtable_kernel(const __grid_constant__ Problem pb, double* gtab) {
+    const int HW = pb.H * pb.W;
+    const int sc = blockIdx.x;                         // cube * HW + site
+    const int cube = sc / HW, site = sc - cube * HW;
+    const int y = site / pb.W, x = site - y * pb.W;
+    const T* iv = IVCUBE ? (const T*)pb.iv + (size_t)cube * HW * pb.Dp : nullptr;
+    const double ivs = IVCUBE ? 0.0 : pb.iv_scalar[cube];
+    for (int z = threadIdx.x; z < pb.Dp; z += blockDim.x) {
+        double g = 0.0;
+        for (int i = 0; i < pb.fh; ++i) {
+            const int Y = y - pb.fhh + i;
+            if (Y < 0 || Y >= pb.H) continue;
+            for (int k = 0; k < pb.fw; ++k) {
+                const int X = x - pb.fhw + k;
+                if (X < 0 || X >= pb.W) continue;
+                const double f = pb.fsf[i * pb.fw + k];
+                const double w = IVCUBE ? (double)iv[((size_t)Y * pb.W + X) * pb.Dp + z] : ivs;
+                g = fma(f * f, w, g);
+            }
+        }
+        gtab[(size_t)sc * pb.Dp + z] = z < pb.D ? g : 0.0;
+    }
+}
+
 template <typename T, bool IVCUBE, int NE>
 __global__ void __launch_bounds__(384, 1)
 sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, long long it1_all,
@@ -264,15 +320,13 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                 // ---- window sums (registers only) -------------------------------------
                 const int dx = heldX - xl;                       // FSF column, valid if active
                 const bool active = wt && dx >= 0 && dx < fw && heldX >= 0 && heldX < W;
-                double part[8];
+                double pB = 0.0, pPO = 0.0;
+                double h[VEC];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) part[k] = 0.0;
-                double h[VEC], g[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
+                for (int v = 0; v < VEC; ++v) h[v] = 0.0;
                 const double* fcol = sm.F + (active ? dx : 0);
                 if (active) {
-                    double f2 = 0.0;
+                    // h[z] only: G[z] comes from the table (gtable_kernel), warp B forms its sums
 #pragma unroll
                     for (int i = 0; i < NE; ++i) {
                         if (i < fh) {
@@ -282,25 +336,17 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                             if (IVCUBE) {
                                 double w_[VEC];
                                 unpack(ivcache[i], w_);
-                                const double ff = f * f;
 #pragma unroll
-                                for (int v = 0; v < VEC; ++v) {
-                                    h[v] = fma(f * w_[v], e[v], h[v]);
-                                    g[v] = fma(ff, w_[v], g[v]);
-                                }
+                                for (int v = 0; v < VEC; ++v) h[v] = fma(f * w_[v], e[v], h[v]);
                             } else {
-                                // rows outside the cube hold e = 0 but must not count in F^2
-                                const int Y = y - fhh + i;
-                                const double fin = (Y >= 0 && Y < H) ? f : 0.0;
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) h[v] = fma(f, e[v], h[v]);
-                                f2 = fma(fin, fin, f2);
                             }
                         }
                     }
                     if (!IVCUBE) {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) { h[v] *= ivs; g[v] = ivs * f2; }
+                        for (int v = 0; v < VEC; ++v) h[v] *= ivs;
                     }
                 }
                 if (warp == 0) PH_ADD(0);                        // [0] W switch + sums
@@ -313,18 +359,13 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                     lo_v[v] = Lu_o[zp * VEC + v];
                     ln_v[v] = Lu_n[zp * VEC + v];
                     if (active) {
-                        const double dl = lo_v[v] - ln_v[v];
-                        part[R_B] = fma(dl, h[v], part[R_B]);
-                        part[R_PO] = fma(lo_v[v], h[v], part[R_PO]);
-                        part[R_C] = fma(dl * dl, g[v], part[R_C]);
-                        part[R_QOO] = fma(lo_v[v] * lo_v[v], g[v], part[R_QOO]);
-                        part[R_QON] = fma(lo_v[v] * ln_v[v], g[v], part[R_QON]);
-                        part[R_QNN] = fma(ln_v[v] * ln_v[v], g[v], part[R_QNN]);
+                        pB = fma(lo_v[v] - ln_v[v], h[v], pB);
+                        pPO = fma(lo_v[v], h[v], pPO);
                     }
                 }
                 {
-                    const double tot = warp_sum8(part, lane);
-                    if ((lane & 3) == 0) sm.red[warp * 8 + warp_sum8_slot(lane)] = tot;
+                    const double tot = warp_sum2(pB, pPO, lane);
+                    if ((lane & 15) == 0) sm.red[warp * 2 + (lane >> 4)] = tot;
                 }
                 if (warp == 0) PH_ADD(2);                        // [2] W partials
                 TRW(3);
@@ -357,16 +398,37 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
                 TRD(5, reinterpret_cast<const double&>(ecache[0]));
                 if (j + 2 < ns) bar_arrive_named(4 + par, cntAll);   // FREE: buffers of site j
             } else if (roleB) {
+                // G[z] of this site (static table); the loads fly while B waits for the profiles
+                const double* gt = pb.gtab + ((size_t)cube * HW + site) * Dp;
+                const double g0 = lane < Dp ? gt[lane] : 0.0;
+                const double g1 = lane + 32 < Dp ? gt[lane + 32] : 0.0;
                 bar_sync_named(2 + par, cntAll);
+                // quadratic sums over G (C, QOO, QON, QNN of d3d_kernels.cuh): they need the two
+                // line profiles only, so B forms them while the window warps reduce h
+                double qs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+                for (int z = lane; z < Dp; z += 32) {
+                    const double G = z < 32 ? g0 : (z < 64 ? g1 : gt[z]);
+                    const double lo = Lu_o[z], ln = Lu_n[z], dl = lo - ln;
+                    qs[0] = fma(dl * dl, G, qs[0]);
+                    qs[1] = fma(lo * lo, G, qs[1]);
+                    qs[2] = fma(lo * ln, G, qs[2]);
+                    qs[3] = fma(ln * ln, G, qs[3]);
+                }
+                const double qr = warp_sum4(qs, lane);
                 bar_sync_named(6, cntWB);
                 PH_ADD(6);                                       // [6] B waits
-                // totals: lane s < 8 owns slot s and adds the nww warp partials
+                // totals: lanes 0, 1 add the nww warp partials of the two sums over h
                 double t = 0.0;
-                if (lane < 8)
-                    for (int wv = 0; wv < nww; ++wv) t += sm.red[wv * 8 + lane];
+                if (lane < 2)
+                    for (int wv = 0; wv < nww; ++wv) t += sm.red[wv * 2 + lane];
                 double tot[R_N];
-#pragma unroll
-                for (int k = 0; k < R_N; ++k) tot[k] = __shfl_sync(0xffffffffu, t, k);
+                tot[R_B] = __shfl_sync(0xffffffffu, t, 0);
+                tot[R_PO] = __shfl_sync(0xffffffffu, t, 1);
+                tot[R_C] = __shfl_sync(0xffffffffu, qr, 0);
+                tot[R_QOO] = __shfl_sync(0xffffffffu, qr, 16);
+                tot[R_QON] = __shfl_sync(0xffffffffu, qr, 8);
+                tot[R_QNN] = __shfl_sync(0xffffffffu, qr, 24);
                 const double a = prop_s[0], c_old = prop_s[1], w_old = prop_s[2];
                 const double a_new = prop_s[3], c_new = prop_s[4], w_new = prop_s[5];
                 const bool oob = prop_s[7] != 0.0;
