@@ -240,6 +240,27 @@ def _cpu_chain(args):
 
 
 # ----------------------------------------------------------------------------------
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """Libraries may write to stdout (NCCL prints its version line there when NCCL_DEBUG is set):
+    send everything to stderr until the result line, so that stdout carries ONE JSON line."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line))
+    sys.stdout.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -257,6 +278,7 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--cpu-sweeps', type=int, default=None)
     args = ap.parse_args()
+    quiet_stdout()
     args.warmup = max(args.warmup, 0)
 
     rank = int(os.environ.get('RANK', '0'))
@@ -294,7 +316,7 @@ def main():
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'sweeps_per_s': v / (wl['H'] * wl['W']),
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -419,7 +441,7 @@ def main():
             'sample': '1 chain, %d timed sweeps (%d site updates) of the same cube on one host core '
                       '(numpy is single-threaded on this path); host has %d cores'
                       % (cs - 1, upd, os.cpu_count() or 1)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -554,7 +576,7 @@ def bench_tiled(args, rank, local_rank, world, sweeps):
                 'ms_per_step': e2e_s * 1e3, 'setup_s': setup_s,
                 'api': 'TiledSweeper.sweep(..., chain_out, lik_out)'},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
