@@ -336,7 +336,10 @@ def main():
     mode = _native.SEQ_EXACT if args.mode == 'sequential' else _native.COLOURED
 
     ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
-    stream = torch.cuda.current_stream()
+    # an explicit stream: the legacy default stream has handle 0, which d3d_ctx_set_stream reads
+    # as "use the library's own stream" -- events and the L2 flush would then be unordered with
+    # the sweep kernels
+    stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_rtnorm_tables(*rtnorm_tables.tables())
     ctx.set_rng(42, rank * n_chains)
@@ -363,7 +366,8 @@ def main():
     barrier()
     with ClockSampler(local_rank) as clocks:
         for _ in range(args.steps):
-            flush.fill_(1)                       # L2 flush between timed iterations
+            with torch.cuda.stream(stream):
+                flush.fill_(1)                   # L2 flush between timed iterations (same stream)
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)

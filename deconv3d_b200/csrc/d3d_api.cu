@@ -142,6 +142,7 @@ struct d3d_ctx {
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
     static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
     void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
+    long long sched_C = -1, sched_S = -1; int sched_G = -1, sched_max_items = 1; size_t sched_flat = 0;
     bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
     bool colour_attr_set = false, apply_attr_set = false;
     bool cluster_attr_set = false, apply_cluster_attr_set = false;
@@ -244,7 +245,7 @@ extern "C" int d3d_ctx_synchronize(d3d_ctx* c) {
 // ------------------------------------------------------------------------------
 template <typename T>
 static int ingest(d3d_ctx* c, const double* src_any, const double* nan_src_dev, void* dst, int n,
-                  int mode, double** staged_out) {
+                  int mode, double** staged_out, int* nan_seen = nullptr) {
     const Problem& pb = c->pb;
     size_t cnt = (size_t)n * pb.D * pb.H * pb.W;
     double* stage = nullptr;
@@ -253,7 +254,7 @@ static int ingest(d3d_ctx* c, const double* src_any, const double* nan_src_dev, 
     if (e != cudaSuccess) { dev_free(stage); return fail(D3D_ECUDA, "copy of cube failed: %s", cudaGetErrorString(e)); }
     long long blocks = (long long)n * pb.H * ((pb.Dp + 31) / 32) * ((pb.W + 31) / 32);
     ingest_kernel<T><<<(unsigned)blocks, 256, 0, c->stream>>>(stage, nan_src_dev, (T*)dst, n, pb.D,
-                                                              pb.Dp, pb.H, pb.W, mode);
+                                                              pb.Dp, pb.H, pb.W, mode, nan_seen);
     c->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) { dev_free(stage); return fail(D3D_ECUDA, "ingest launch failed: %s", cudaGetErrorString(e)); }
@@ -343,9 +344,25 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     if ((rc = dalloc(c, &d_err, (size_t)pb.n_chains * cube_elems * c->elem()))) return rc;
     CK(cudaMemsetAsync(d_err, 0, (size_t)pb.n_chains * cube_elems * c->elem(), c->stream));
     double* staged_data = nullptr;
-    if (c->dtype == D3D_F64) rc = ingest<double>(c, data, nullptr, d_data, n_cubes, 0, &staged_data);
-    else rc = ingest<float>(c, data, nullptr, d_data, n_cubes, 0, &staged_data);
+    int* d_nan = nullptr;
+    if ((rc = dalloc(c, &d_nan, sizeof(int)))) return rc;
+    CK(cudaMemsetAsync(d_nan, 0, sizeof(int), c->stream));
+    if (c->dtype == D3D_F64) rc = ingest<double>(c, data, nullptr, d_data, n_cubes, 0, &staged_data, d_nan);
+    else rc = ingest<float>(c, data, nullptr, d_data, n_cubes, 0, &staged_data, d_nan);
     if (rc) return rc;
+    if (!pb.var_is_cube) {
+        // NaN voxels must drop out of the chi2 sums (nansum, lib/run.py:24-27, 420-425): that needs
+        // per-voxel weights, which a scalar variance does not carry -- refuse instead of silently
+        // giving such voxels the value 0 with full weight
+        int h_nan = 0;
+        CK(cudaMemcpyAsync(&h_nan, d_nan, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (h_nan) {
+            dev_free(staged_data);
+            return fail(D3D_EINVAL, "d3d_set_problem: the data holds NaN voxels; pass the variance as a cube "
+                                    "(D3D_VAR_CUBE) so that they get zero weight");
+        }
+    }
     double* d_ivs = nullptr;
     if (pb.var_is_cube) {
         if ((rc = dalloc(c, &d_iv, (size_t)n_cubes * cube_elems * c->elem()))) { dev_free(staged_data); return rc; }
@@ -889,6 +906,11 @@ extern "C" int d3d_delta_logl(d3d_ctx* c, int chain, int y, int x, const double 
 }
 
 // ------------------------------------------------------------------------------
+__global__ void fill_ll_kernel(long long* p, int n, long long v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 template <typename T, bool IV, int NE>
 static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep, double min_rate,
                               double* chain_dev, double* lik_dev, long long row_first,
@@ -912,46 +934,57 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
         const long long S = it1 - it0;
         if (C > sms && S > 0 && !getenv("D3D_NO_BALANCE")) {
             const int G = sms;
-            const long long Tslots = (C * S + G - 1) / G;       // sweeps per CTA
-            std::vector<std::vector<int4>> lists(G);
-            int g = 0; long long used = 0;
-            for (int ch = 0; ch < C; ++ch) {
-                long long room = Tslots - used;
-                if (room >= S) {                                // whole chain on CTA g
-                    lists[g].push_back(make_int4(ch, 0, (int)S, 0));
-                    used += S;
-                    if (used == Tslots && g + 1 < G) { ++g; used = 0; }
-                } else {
-                    // split: the LATE slots of CTA g take the chain's last `room` sweeps, the
-                    // EARLY slots of CTA g+1 its first S-room sweeps
-                    if (room > 0) lists[g].push_back(make_int4(ch, (int)(S - room), (int)S, 0));
-                    ++g; used = 0;
-                    lists[g].insert(lists[g].begin(), make_int4(ch, 0, (int)(S - room), 0));
-                    used = S - room;
+            // the work-item lists depend on (chains, sweeps, CTAs) only: built and uploaded once,
+            // then re-used by every call of the same shape (no host synchronisation per call);
+            // the hand-over counters are reset on the stream by a one-block kernel
+            if (c->sched_C != C || c->sched_S != S || c->sched_G != G) {
+                const long long Tslots = (C * S + G - 1) / G;       // sweeps per CTA
+                std::vector<std::vector<int4>> lists(G);
+                int g = 0; long long used = 0;
+                for (int ch = 0; ch < C; ++ch) {
+                    long long room = Tslots - used;
+                    if (room >= S) {                                // whole chain on CTA g
+                        lists[g].push_back(make_int4(ch, 0, (int)S, 0));
+                        used += S;
+                        if (used == Tslots && g + 1 < G) { ++g; used = 0; }
+                    } else {
+                        // split: the LATE slots of CTA g take the chain's last `room` sweeps, the
+                        // EARLY slots of CTA g+1 its first S-room sweeps
+                        if (room > 0) lists[g].push_back(make_int4(ch, (int)(S - room), (int)S, 0));
+                        ++g; used = 0;
+                        lists[g].insert(lists[g].begin(), make_int4(ch, 0, (int)(S - room), 0));
+                        used = S - room;
+                    }
                 }
+                int max_items = 1;
+                for (auto& l : lists) max_items = std::max(max_items, (int)l.size());
+                std::vector<int4> flat((size_t)G * max_items, make_int4(0, 0, 0, 0));
+                std::vector<int> cnt(G);
+                for (int q = 0; q < G; ++q) {
+                    cnt[q] = (int)lists[q].size();
+                    for (size_t k = 0; k < lists[q].size(); ++k) flat[(size_t)q * max_items + k] = lists[q][k];
+                }
+                const size_t need = flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long);
+                if (c->sched_cap < need) {
+                    if (c->d_sched) { cudaStreamSynchronize(c->stream); dev_free(c->d_sched); }
+                    c->sched_cap = 2 * need;
+                    if (dev_malloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; c->sched_C = -1; return cudaErrorMemoryAllocation; }
+                }
+                char* base = (char*)c->d_sched;
+                cudaMemcpyAsync(base, flat.data(), flat.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream);
+                cudaMemcpyAsync(base + flat.size() * sizeof(int4) + C * sizeof(long long), cnt.data(),
+                                G * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+                cudaStreamSynchronize(c->stream);       // host vectors go out of scope (first call of a shape only)
+                c->sched_C = C; c->sched_S = S; c->sched_G = G;
+                c->sched_max_items = max_items; c->sched_flat = flat.size();
             }
-            int max_items = 1;
-            for (auto& l : lists) max_items = std::max(max_items, (int)l.size());
-            std::vector<int4> flat((size_t)G * max_items, make_int4(0, 0, 0, 0));
-            std::vector<int> cnt(G);
-            for (int q = 0; q < G; ++q) {
-                cnt[q] = (int)lists[q].size();
-                for (size_t k = 0; k < lists[q].size(); ++k) flat[(size_t)q * max_items + k] = lists[q][k];
-            }
-            std::vector<long long> prog(C, it0);
-            if (c->sched_cap < flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long)) {
-                if (c->d_sched) dev_free(c->d_sched);
-                c->sched_cap = 2 * (flat.size() * sizeof(int4) + G * sizeof(int) + C * sizeof(long long));
-                if (dev_malloc(&c->d_sched, c->sched_cap) != cudaSuccess) { c->d_sched = nullptr; c->sched_cap = 0; return cudaErrorMemoryAllocation; }
-            }
+            const int max_items = c->sched_max_items;
             char* base = (char*)c->d_sched;
             int4* d_items = (int4*)base;
-            long long* d_prog = (long long*)(base + flat.size() * sizeof(int4));
-            int* d_cnt = (int*)(base + flat.size() * sizeof(int4) + C * sizeof(long long));
-            cudaMemcpyAsync(d_items, flat.data(), flat.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream);
-            cudaMemcpyAsync(d_prog, prog.data(), C * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
-            cudaMemcpyAsync(d_cnt, cnt.data(), G * sizeof(int), cudaMemcpyHostToDevice, c->stream);
-            cudaStreamSynchronize(c->stream);       // host vectors go out of scope
+            long long* d_prog = (long long*)(base + c->sched_flat * sizeof(int4));
+            int* d_cnt = (int*)(base + c->sched_flat * sizeof(int4) + C * sizeof(long long));
+            fill_ll_kernel<<<(C + 255) / 256, 256, 0, c->stream>>>(d_prog, C, it0);
+            c->launches++;
             sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<G, c->slide_threads, c->slide_smem, c->stream>>>(
                 c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local,
                 d_items, d_cnt, max_items, d_prog);
@@ -1184,7 +1217,8 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
     for (int k = 0; k < pb.n_chains; ++k) {
         if (accepted_out) accepted_out[k] = h_acc[k];
         if (iterations_out) iterations_out[k] = h_it[k];
-        updates += (h_it[k] - it_begin) * (long long)c->h_nsites[k / pb.chains_per_cube];
+        // (a chain stopped by the acceptance-rate test in an earlier call has h_it < it_begin)
+        updates += std::max(0LL, h_it[k] - it_begin) * (long long)c->h_nsites[k / pb.chains_per_cube];
     }
     c->last_updates = updates;
     c->last_bytes = (int64_t)((pb.var_is_cube ? 3 : 2) * (double)c->elem() *
@@ -1376,6 +1410,13 @@ extern "C" int d3d_tile_fused_init(d3d_ctx* c, int n_tiles, int my_index, void**
     c->tb.flags[my_index] = (unsigned long long*)c->box;
     c->tb.inbox[my_index] = (double*)((char*)c->box + box_flag_bytes());
     c->tb.done_counter = (unsigned int*)((char*)c->box + TILE_MAXW * sizeof(unsigned long long));
+    {   // bound of the flag wait: long enough for a healthy but slow peer (Python-driven ranks
+        // pause on parameter copies, lazy module loading); D3D_TILE_TIMEOUT_S overrides
+        double secs = 30.0;
+        if (const char* e = getenv("D3D_TILE_TIMEOUT_S")) secs = atof(e) > 0 ? atof(e) : secs;
+        c->tb.timeout_cycles = (long long)(secs * 2.0e9);
+    }
+    CK(cudaMemset(c->pb.status, 0, sizeof(int)));            // a fresh exchange forgets an earlier time-out
     if (box_out) *box_out = c->box;
     if (box_bytes) *box_bytes = (int64_t)bytes;
     return 0;

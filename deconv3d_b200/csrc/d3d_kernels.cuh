@@ -1303,7 +1303,7 @@ __global__ void clean_kernel(const __grid_constant__ Problem pb, const double* p
 // ---------------------------------------------------------------------------
 template <typename T>
 __global__ void ingest_kernel(const double* src, const double* data_for_nan, T* dst, int n, int D,
-                              int Dp, int H, int W, int mode) {
+                              int Dp, int H, int W, int mode, int* nan_seen = nullptr) {
     // tile transpose through shared memory: read x-fastest, write z-fastest
     __shared__ double tile[32][33];
     const int nzt = (Dp + 31) / 32, nxt = (W + 31) / 32;
@@ -1324,7 +1324,7 @@ __global__ void ingest_kernel(const double* src, const double* data_for_nan, T* 
                 double dv = data_for_nan ? data_for_nan[si] : 0.0;
                 v = (v == v && dv == dv) ? 1.0 / v : 0.0;
                 if (!(v == v) || isinf(v)) v = 0.0;
-            } else if (!(v == v)) v = 0.0;
+            } else if (!(v == v)) { v = 0.0; if (nan_seen) *nan_seen = 1; }
         }
         tile[r][tx] = v;
     }

@@ -162,6 +162,16 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
     // rule, so that every SM gets the same number of sweeps; a chain split over two CTAs is
     // handed over through `progress` (both CTAs are resident: grid <= number of SMs).
     const int n_items = items ? item_count[blockIdx.x] : 1;
+    // truncated-normal tables (lib/rtnorm.py:227-2681) in shared memory for the inline table
+    // branch of warp B: x[4002], yu[4001] as doubles, ncell[8961] as 16-bit.  Copied once per
+    // CTA, BEFORE the item loop: an item whose chain was stopped earlier skips the loop body.
+    double* const tx = smem_raw + smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp);
+    double* const tyu = tx + 4002;
+    unsigned short* const tnc = (unsigned short*)(tyu + 4002);
+    for (int q = threadIdx.x; q < 4002; q += blockDim.x) tx[q] = pb.rt.x[q];
+    for (int q = threadIdx.x; q < 4001; q += blockDim.x) tyu[q] = pb.rt.yu[q];
+    for (int q = threadIdx.x; q < 8961; q += blockDim.x) tnc[q] = (unsigned short)pb.rt.ncell[q];
+    __syncthreads();
   for (int item = 0; item < n_items; ++item) {
     int chain; long long it0, it1;
     if (items) {
@@ -220,18 +230,6 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
     const size_t rstride = (size_t)W * Dp;
     T* const errT = (T*)err;
     const T* const ivT = (const T*)ivc;
-
-    // truncated-normal tables (lib/rtnorm.py:227-2681) in shared memory for the inline table
-    // branch of warp B: x[4002], yu[4001] as doubles, ncell[8961] as 16-bit
-    double* const tx = smem_raw + smem_doubles(fh, fw, pb.P, Dp);
-    double* const tyu = tx + 4002;
-    unsigned short* const tnc = (unsigned short*)(tyu + 4002);
-    if (item == 0) {
-        for (int q = threadIdx.x; q < 4002; q += blockDim.x) tx[q] = pb.rt.x[q];
-        for (int q = threadIdx.x; q < 4001; q += blockDim.x) tyu[q] = pb.rt.yu[q];
-        for (int q = threadIdx.x; q < 8961; q += blockDim.x) tnc[q] = (unsigned short)pb.rt.ncell[q];
-        __syncthreads();
-    }
 
     double rate = pb.rate[chain];
     long long accepted = pb.accepted[chain];       // owned by lane 0 of warp B

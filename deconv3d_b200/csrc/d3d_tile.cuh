@@ -433,6 +433,7 @@ struct TileBox {
     unsigned long long* flags[TILE_MAXW];   // flags array of every box (peer pointers)
     double* inbox[TILE_MAXW];               // inbox of every box
     unsigned int* done_counter;             // local: blocks of push_records_kernel that finished
+    long long timeout_cycles;               // bound of the flag wait (D3D_TILE_TIMEOUT_S, default 30 s)
 };
 
 __device__ __forceinline__ size_t tile_inbox_index(const TileBox& tb, int parity, int src, long long slot) {
@@ -486,7 +487,7 @@ __global__ void push_records_kernel(const __grid_constant__ Problem pb, const __
     }
 }
 
-// Waits (bounded: ~2 s) until source tile `src` has published `phase`; returns false on timeout.
+// Waits (bounded: tb.timeout_cycles) until source tile `src` has published `phase`; returns false on timeout.
 __device__ __forceinline__ bool tile_wait_flag(const TileBox& tb, int src, unsigned long long phase) {
     const unsigned long long* f = tb.flags[tb.my_tile] + src;
     const long long t0 = clock64();
@@ -494,7 +495,7 @@ __device__ __forceinline__ bool tile_wait_flag(const TileBox& tb, int src, unsig
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         if (v >= phase + 1ull) return true;
-        if (clock64() - t0 > 4000000000LL) return false;
+        if (clock64() - t0 > tb.timeout_cycles) return false;
         __nanosleep(200);
     }
 }
@@ -517,11 +518,21 @@ apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ Til
     if (src == tb.my_tile) return;                           // (whole cluster)
     __shared__ int s_ok;
     // (after one time-out every later applier gives up at once: a dead peer costs seconds, not
-    // seconds per phase)
-    if (threadIdx.x == 0)
+    // seconds per phase).  In a cluster the LEADER alone decides and shares its verdict through
+    // DSMEM, so that either all CTAs of the cluster go on to the cluster barrier below or none.
+    if (threadIdx.x == 0 && cr == 0)
         s_ok = (*(volatile int*)pb.status != 2 && tile_wait_flag(tb, src, phase)) ? 1 : 0;
-    __syncthreads();
-    if (!s_ok) { if (threadIdx.x == 0) atomicExch(pb.status, 2); return; }   // (flag state is the same for the cluster... see below)
+    int ok;
+    if (CLUSTER) {
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        ok = *cluster.map_shared_rank(&s_ok, 0);
+        cluster.sync();                                      // the leader's s_ok stays alive until read
+    } else {
+        __syncthreads();
+        ok = s_ok;
+    }
+    if (!ok) { if (threadIdx.x == 0) atomicExch(pb.status, 2); return; }
     const double* rp = tb.inbox[tb.my_tile] + tile_inbox_index(tb, (int)(phase & 1ull), src, ridx - (long long)src * tb.slots);
     double r[REC_N];
 #pragma unroll

@@ -198,6 +198,9 @@ class Run(object):
             first_row = ctx.get_params()
         if chain_on_device:
             chains[:, 0] = torch.from_numpy(first_row).to(tdev)
+            # torch works on its own (legacy default) stream, the library on a non-blocking one:
+            # order the two explicitly before the library touches the tensors
+            torch.cuda.synchronize(tdev)
         else:
             chains[:, 0] = first_row
 
@@ -231,6 +234,7 @@ class Run(object):
             if chain_on_device:
                 off_t = torch.from_numpy(off).to(tdev)
                 chains[:, 1:, off_t] = chains[:, :1, off_t]
+                torch.cuda.synchronize(tdev)            # before d3d_chain_mean reads the rows
             else:
                 chains[:, 1:, off] = chains[:, :1, off]
 

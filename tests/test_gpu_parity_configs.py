@@ -1,0 +1,257 @@
+"""
+GPU <-> oracle parity ON THE CONFIGURATIONS THAT ARE BENCHED (run with ``-m gpu`` on a B200).
+
+tests/test_gpu_parity.py pins the kernels on small cases; here the oracle
+(oracle.reference_port.run_chain, the literal restatement of lib/run.py:367-519, fed by the
+same Philox stream) follows the full-size BASELINE.json configurations for a few sweeps:
+
+  (i)   the exact problem of ``bench.build_workload('cfg2x256')`` -- 40^3, Moffat 13x13, variance
+        cube, row-major order, 256 chains in one balanced launch -- chains 0, 147, 148, 255
+        (first / last chain of the first wave of SMs, first / last chain that is handed over);
+  (ii)  one cfg5 galaxy (32^3, FSF 11x11, its own data + variance) inside a multi-galaxy context;
+  (iii) cfg3: the cfg2 cube in COLOURED mode at full size, oracle run in colour-class order;
+  (iv)  cfg2 with the 21x21 stamp (SURVEY.md 8d "secondary");
+  (v)   a D = 64 cube (P = 64: full spectral wrap, cfg4's depth).
+
+Bar (BASELINE.json north_star): identical accept/reject decisions proposal by proposal, chains
+to 1e-9, per-proposal delta-logL to 1e-6 relative, final residual to 1e-9 max|data|.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nat():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail('these tests need a CUDA device (there is no CPU fallback)')
+    from deconv3d_b200 import _native
+    return _native
+
+
+def _tables():
+    from deconv3d_b200 import rtnorm_tables
+    x, yu, nc = rtnorm_tables.tables()
+    return x, yu, nc.astype(np.int64)
+
+
+def _check_chain(ref, trace, chain, lik, acc, its, residual, data, keep=1, rtol=1e-9):
+    """One device chain (rows [n_saved,H,W,3]) against one oracle run of the same stream."""
+    m = ref['mask'] == 1
+    H, W = m.shape
+    assert its == ref['iterations']
+    n_acc_ref = sum(1 for v in trace.values() if v[3])
+    assert acc - m.sum() == n_acc_ref, (acc, n_acc_ref)
+    max_it = ref['iterations']
+    if keep == 1:
+        for it in range(1, max_it):
+            moved = (chain[it, :, :, 1] != chain[it - 1, :, :, 1]) | \
+                    (chain[it, :, :, 2] != chain[it - 1, :, :, 2])
+            ref_acc = np.zeros((H, W), bool)
+            for (y, x) in zip(*np.nonzero(m)):
+                ref_acc[y, x] = trace[(it, y, x)][3]
+            assert np.array_equal(moved & m, ref_acc), 'decisions differ at iteration %d' % it
+    scale = np.abs(ref['chain'][:, m]).max()
+    ok = np.ones(ref['chain'].shape, bool)
+    for (it, y, x), v in trace.items():            # degenerate draws, see test_gpu_parity._compare_chain
+        mu, ro = v[5], v[6]
+        if it % keep == 0 and abs(mu) <= 1e-9 * np.sqrt(ro):
+            ok[it // keep, y, x, 0] = False
+    assert (~ok).sum() <= 0.005 * ok.size
+    sel = ok & m[None, :, :, None]
+    np.testing.assert_allclose(chain[sel], ref['chain'][sel], rtol=rtol, atol=1e-12 * scale)
+    np.testing.assert_allclose(lik[1:, m], ref['likelihoods'][1:, m], rtol=max(rtol, 1e-6), atol=1e-9)
+    if residual is not None:
+        np.testing.assert_allclose(residual, ref['err'], rtol=0, atol=1e-9 * np.abs(data).max())
+
+
+def _oracle_chain(data, var, fsf, lsf, seed, chain_id, init, max_it, order=None, prior=None):
+    from oracle import reference_port as port, streams
+    trace = {}
+    ref = port.run_chain(data, fsf, lsf, streams.PhiloxStream(seed, chain_id),
+                         variance_cube=var, initial_parameters=init,
+                         gibbs_apriori_variance=prior, max_iterations=max_it, trace=trace,
+                         rtnorm_tables=_tables(), site_order=order, min_acceptance_rate=0.0,
+                         refresh_every=0)
+    return ref, trace
+
+
+def _bench_arrays(name, chains):
+    import bench
+    wl = bench.build_workload(name, chains)
+    return wl, bench.realise(wl, 0)
+
+
+def _device_run(nat, arrays, chains_per_cube, max_it, mode, seed=42, first_chain=0, n_cubes=1):
+    ctx = nat.Context(0, nat.F64)
+    ctx.set_rtnorm_tables(*_tables())
+    ctx.set_rng(seed, first_chain)
+    ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                    arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=chains_per_cube)
+    ctx.init_params_uniform()
+    n = n_cubes * chains_per_cube
+    D, H, W = arrays['data'].shape[-3:]
+    chain = np.zeros((n, max_it, H, W, 3))
+    lik = np.zeros((n, max_it, H, W))
+    chain[:, 0] = ctx.get_params()
+    ctx.forward(write_err=True)
+    acc, its, _ = ctx.sweep(1, max_it - 1, mode=mode, refresh_every=1000, min_acceptance_rate=0.0,
+                            chain_out=chain, lik_out=lik)
+    res = ctx.get_residual()
+    ctx.close()
+    return chain, lik, acc, its, res
+
+
+def test_cfg2x256_benched_launch_vs_oracle(nat):
+    """(i) The headline workload itself: 256 chains, balanced (wrap-around) launch of the
+    sliding-window kernel <double, variance cube, 13 rows>, row-major order."""
+    wl, arrays = _bench_arrays('cfg2x256', 256)
+    max_it = 4
+    chain, lik, acc, its, res = _device_run(nat, arrays, 256, max_it, nat.SEQ_EXACT)
+    for k in (0, 147, 148, 255):
+        ref, trace = _oracle_chain(arrays['data'][0], arrays['var'][0], arrays['fsf'], arrays['lsf'],
+                                   42, k, chain[k, 0], max_it, prior=float(arrays['prior'][0]))
+        _check_chain(ref, trace, chain[k], lik[k], int(acc[k]), int(its[k]), res[k], arrays['data'][0])
+
+
+def test_cfg5_galaxy_vs_oracle(nat):
+    """(ii) Survey batch: galaxy 2 of a 3-galaxy context (32^3, FSF 11x11, own data/variance)."""
+    wl, arrays = _bench_arrays('cfg5', 3)
+    max_it = 4
+    chain, lik, acc, its, res = _device_run(nat, arrays, 1, max_it, nat.SEQ_EXACT, n_cubes=3)
+    g = 2
+    ref, trace = _oracle_chain(arrays['data'][g], arrays['var'][g], arrays['fsf'], arrays['lsf'],
+                               42, g, chain[g, 0], max_it, prior=float(arrays['prior'][g]))
+    # boundaries of the context = the reference's own for that galaxy
+    np.testing.assert_allclose(ref['max_boundaries'], arrays['pmax'][g])
+    _check_chain(ref, trace, chain[g], lik[g], int(acc[g]), int(its[g]), res[g], arrays['data'][g])
+
+
+@pytest.mark.parametrize('by_chain', ['0', '1'])
+def test_cfg3_coloured_full_size_vs_oracle(nat, monkeypatch, by_chain):
+    """(iii) cfg3: colour-class order at full size, both schedules (launch per class / chain per
+    CTA on the colour-ordered site list)."""
+    from oracle import reference_port as port
+    monkeypatch.setenv('D3D_COLOUR_BY_CHAIN', by_chain)
+    wl, arrays = _bench_arrays('cfg2x256', 2)
+    max_it = 3
+    chain, lik, acc, its, res = _device_run(nat, arrays, 2, max_it, nat.COLOURED)
+    fh, fw = arrays['fsf'].shape
+    order = port.colour_class_order(np.ones((40, 40)), fh, fw)
+    k = 1
+    ref, trace = _oracle_chain(arrays['data'][0], arrays['var'][0], arrays['fsf'], arrays['lsf'],
+                               42, k, chain[k, 0], max_it, order=order, prior=float(arrays['prior'][0]))
+    _check_chain(ref, trace, chain[k], lik[k], int(acc[k]), int(its[k]), res[k], arrays['data'][0])
+
+
+def test_cfg2_fsf21_vs_oracle(nat):
+    """(iv) cfg2 with the Moffat stamp truncated to 21x21."""
+    from deconv3d_b200 import synthetic
+    import bench
+    wl = bench.build_workload('cfg2', 1)
+    wl['inst'] = synthetic.muse_wfm_instrument('moffat', 21)
+    arrays = bench.realise(wl, 0)
+    assert arrays['fsf'].shape == (21, 21)
+    max_it = 3
+    chain, lik, acc, its, res = _device_run(nat, arrays, 1, max_it, nat.SEQ_EXACT)
+    ref, trace = _oracle_chain(arrays['data'][0], arrays['var'][0], arrays['fsf'], arrays['lsf'],
+                               42, 0, chain[0, 0], max_it, prior=float(arrays['prior'][0]))
+    _check_chain(ref, trace, chain[0], lik[0], int(acc[0]), int(its[0]), res[0], arrays['data'][0])
+
+
+@pytest.mark.parametrize('fsf_size', [13, 21])
+def test_depth64_vs_oracle(nat, fsf_size):
+    """(v) D = 64 (P = 64: every channel wraps, cfg4's depth) on a 20x22 field."""
+    from deconv3d_b200 import synthetic, MUSE
+    from oracle import reference_port as port
+    D, H, W = 64, 20, 22
+    inst = synthetic.muse_wfm_instrument('moffat', fsf_size)
+    cube0 = MUSE().build_cube(np.zeros((D, H, W)))
+    fsf = np.asarray(inst.fsf.as_image(cube0), dtype=np.float64)
+    lsf = inst.lsf.as_vector(cube0)
+    truth = synthetic.halpha_truth(D, H, W)
+    mask = np.ones((H, W))
+    data = -port.compute_error_in_one_step(np.zeros((D, H, W)), truth, fsf, lsf, mask) \
+        + synthetic.noise((D, H, W), 0.05, 77)
+    rs = np.random.RandomState(3)
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    pmax = np.array([[data.max() / fsf.max(), D - 1, D]])
+    arrays = dict(data=data[None], var=var[None], fsf=fsf, lsf=lsf, pmin=np.zeros((1, 3)), pmax=pmax,
+                  prior=pmax[:, 0] ** 2)
+    max_it = 3
+    chain, lik, acc, its, res = _device_run(nat, arrays, 2, max_it, nat.SEQ_EXACT, seed=9)
+    k = 1
+    ref, trace = _oracle_chain(data, var, fsf, lsf, 9, k, chain[k, 0], max_it, prior=float(pmax[0, 0] ** 2))
+    _check_chain(ref, trace, chain[k], lik[k], int(acc[k]), int(its[k]), res[k], data)
+
+
+def test_balanced_schedule_with_stopped_chains(nat):
+    """More chains than SMs, min_acceptance_rate > 0 and chains that stop early, followed by a
+    second d3d_sweep call: a CTA whose FIRST work item is a stopped chain must still serve its
+    remaining chains correctly (the truncated-normal tables are loaded once per CTA, not inside
+    the first item).  Every chain equals its own single-chain run."""
+    from conftest import load_golden
+    g = load_golden('ref_run_A')
+    data, fsf, lsf = g['data'], g['fsf'], g['lsf']
+    from oracle import reference_port as port
+    pmin, pmax = port.single_gaussian_boundaries(data, fsf)
+    n = 333
+
+    def mk(chains, first):
+        ctx = nat.Context(0, nat.F64)
+        ctx.set_rtnorm_tables(*_tables())
+        ctx.set_rng(5, first)
+        # a tiny jump on c, w and a huge one would both do; a high threshold stops chains for sure
+        ctx.set_problem(data, np.array([0.01]), fsf, lsf, pmin, pmax, [0, 0.1, 0.1], float(pmax[0]) ** 2,
+                        chains_per_cube=chains)
+        ctx.init_params_uniform()
+        ctx.forward(write_err=True)
+        return ctx
+
+    H, W = data.shape[1:]
+    ns = H * W
+    # dry run without a threshold, one sweep per call: accepted counts after every sweep give the
+    # acceptance rate every chain will show at every iteration (lib/run.py:356-359)
+    dry = mk(n, 0)
+    A = [np.full(n, ns, dtype=np.int64)]                 # accepted_count starts at n_sites (:341)
+    for it in range(1, 13):
+        a, _, _ = dry.sweep(it, 1, min_acceptance_rate=0.0)
+        A.append(np.array(a, dtype=np.int64))
+    dry.close()
+    # the test before sweep `it` uses the rate formed at it-1: A[it-2] / (ns * (it-1))
+    low = np.min([A[j - 1] / float(ns * j) for j in range(3, 12)], axis=0)
+    srt = np.sort(low)
+    mid = n // 2
+    gaps = srt[mid - 20:mid + 20][1:] - srt[mid - 20:mid + 20][:-1]
+    q = int(np.argmax(gaps))
+    thr = 0.5 * (srt[mid - 20 + q] + srt[mid - 20 + q + 1])   # inside the widest gap near the median
+
+    ctx = mk(n, 0)
+    chain = np.zeros((n, 13, H, W, 3))
+    acc0, its0, _ = ctx.sweep(1, 3, chain_out=chain, min_acceptance_rate=0.0)
+    acc1, its1, _ = ctx.sweep(4, 4, chain_out=chain, min_acceptance_rate=thr)
+    acc2, its2, _ = ctx.sweep(8, 5, chain_out=chain, min_acceptance_rate=thr)
+    stopped = its2 < 13
+    assert stopped.any() and (~stopped).any(), (its2.min(), its2.max())
+    res = ctx.get_residual()
+    picks = [0, 1, 147, 148, 149, 332] + list(np.nonzero(stopped)[0][:3]) + list(np.nonzero(~stopped)[0][:3])
+    for k in sorted(set(int(p) for p in picks)):
+        c1 = mk(1, k)
+        ch = np.zeros((1, 13, H, W, 3))
+        c1.sweep(1, 3, chain_out=ch, min_acceptance_rate=0.0)
+        c1.sweep(4, 4, chain_out=ch, min_acceptance_rate=thr)
+        a1, i1, _ = c1.sweep(8, 5, chain_out=ch, min_acceptance_rate=thr)
+        assert i1[0] == its2[k] and a1[0] == acc2[k], k
+        nrow = int(its2[k])
+        assert np.array_equal(ch[0, 1:nrow], chain[k, 1:nrow]), k
+        assert np.array_equal(c1.get_residual()[0], res[k]), k
+        c1.close()
