@@ -38,14 +38,15 @@ UNIT = 'evals/s'
 def build_workload(name, chains):
     """Returns dict(data [n,D,H,W] builder inputs...) describing the workload on the host."""
     from deconv3d_b200 import synthetic
-    if name in ('cfg2', 'cfg2x256'):
+    if name in ('cfg2', 'cfg2x256', 'cfg2_fsf21'):
         D = H = W = 40
-        inst = synthetic.muse_wfm_instrument('moffat', 13)
+        fs = 21 if name == 'cfg2_fsf21' else 13
+        inst = synthetic.muse_wfm_instrument('moffat', fs)
         truth = synthetic.halpha_truth(D, H, W)
         return dict(name=name, D=D, H=H, W=W, inst=inst, truth=truth[None], n_cubes=1,
                     chains_per_cube=chains, var_kind='cube', sigma=0.05,
                     desc='synthetic MUSE WFM Halpha cube 40x40x40, Moffat FWHM 0.8" beta 2.5 '
-                         '13x13, MUSE LSF, variance cube 0.05^2, %d chain(s)/GPU' % chains)
+                         '%dx%d, MUSE LSF, variance cube 0.05^2, %d chain(s)/GPU' % (fs, fs, chains))
     if name == 'cfg5':
         D = H = W = 32
         inst = synthetic.muse_wfm_instrument('moffat', 11)
@@ -172,6 +173,23 @@ def measured_traffic(workload, chains, sweeps, dtype, mode):
     return None, None
 
 
+def measured_profile():
+    """Issue-slot utilisation of the dominant kernel from the committed ncu --set full capture
+    (profiles/*_sweep_metrics.json, written by profiles/tools/ncu_lines.py --metrics)."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_sweep_metrics.json')), reverse=True):
+        try:
+            t = json.load(open(path))
+            return {'issue_slot_frac': float(t['issue_slot_frac']), 'source': os.path.relpath(path, ROOT)}
+        except Exception:               # noqa: BLE001
+            continue
+    return {}
+
+
+def kernel_name(ctx, mode):
+    return ctx.last_kernel()
+
+
 def measured_peak():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -276,6 +294,7 @@ def main():
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-probes', action='store_true', help='skip the sub-records of the other configurations')
     ap.add_argument('--cpu-sweeps', type=int, default=None)
     args = ap.parse_args()
     quiet_stdout()
@@ -303,7 +322,9 @@ def main():
             v, wall, upd = cpu_reference(args.workload, cs, n_procs)
             per_step.append((v, wall))
         v = float(np.mean([p[0] for p in per_step]))
-        wl = build_workload(args.workload, chains)
+        wl = build_workload(args.workload, n_procs)          # the chains THIS arm runs: one per host core
+        wl['desc'] += ' (reference arm: %d independent chain(s), one process per host core; the GPU arm ' \
+                      'runs %d per GPU on the same cube)' % (n_procs, chains)
         line = {
             'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup,
@@ -397,15 +418,27 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, wl, arrays, rank, local_rank, world, sweeps)
 
+    # cfg4 strong-scaling probe: every rank takes part (the one path with an exchange step)
+    cfg4 = None
+    if args.workload == 'cfg2x256' and args.mode == 'sequential' and not args.no_probes:
+        cfg4 = tiled_probe(args, rank, local_rank, world)
+
     if world > 1 and rank != 0:
         dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak()
     traffic, traffic_src = measured_traffic(args.workload, n_chains, sweeps, args.dtype, args.mode)
+    prof = measured_profile()
     kern_total_ms = float(np.sum(kern_ms))
     achieved = bytes_algo / (kern_total_ms * 1e-3) / 1e9
     state_mb = n_chains * D * H * W * (8 if args.dtype == 'f64' else 4) / 1e6
+    fp64_peak = ctx.fp64_peak()
+    # FP64 work of one site update: per window voxel one multiply + one FMA for the sums and one
+    # FMA for the residual update (5 flop; the O(D) scalar work of the decision is not counted)
+    vox_per_update = (bytes_algo / ((3 if wl['var_kind'] == 'cube' else 2) * (8 if args.dtype == 'f64' else 4))) \
+        / max(1.0, float(updates))
+    fp64_tflops = 5.0 * vox_per_update * float(updates) / (kern_total_ms * 1e-3) / 1e12
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms_max / args.steps,
@@ -419,23 +452,46 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks.summary(),
         'roofline': {
-            'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-            'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src,
+            # The byte model of SURVEY.md 8d (achieved / frac / nominal_hbm_frac) is kept as the
+            # contract asks, but the kernel does not move those bytes: the window lives in
+            # registers.  `bound` names what limits it (ncu: issue slots / dependent latency).
+            'bound': 'issue', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'nominal_hbm_frac': achieved / peak,
+            'traffic': traffic, 'traffic_source': traffic_src,
+            'dram_frac': (traffic / (kern_total_ms / max(1, args.steps) * 1e-3) / 1e9 / peak) if traffic else None,
+            'fp64_pipe_frac': fp64_tflops / fp64_peak, 'fp64_tflops': fp64_tflops,
+            'fp64_peak_tflops': fp64_peak,
+            'issue_slot_frac': prof.get('issue_slot_frac'), 'profile_source': prof.get('source'),
             'peak_source': peak_src,
-            'kernel': 'sweep_seq_slide_kernel' if args.mode == 'sequential' else 'sweep_colour_kernel',
+            'kernel': kernel_name(ctx, args.mode),
             'algorithmic_bytes_per_launch': bytes_algo / max(1, args.steps),
             'kernel_ms_per_launch': kern_total_ms / max(1, args.steps),
             'note': 'achieved = algorithmic bytes / kernel time; algorithmic bytes = (3 with a variance '
                     'cube | 2 with a scalar variance) * s * D * sum_sites wh*ww per chain per sweep '
-                    '(SURVEY.md 8d). The sliding register window re-uses 12 of 13 window columns, so '
-                    'real DRAM traffic (traffic, bytes per launch) is ~300x lower and the kernel is '
-                    'latency-bound, see profiles/r01_notes.md',
+                    '(SURVEY.md 8d). The register-resident window re-uses 12 of 13 window columns, so '
+                    'real DRAM traffic (traffic, dram_frac) is orders of magnitude lower; the kernel '
+                    'is bound by instruction issue and the serial decision chain (issue_slot_frac, '
+                    'fp64_pipe_frac = 5 flop per window voxel against the DFMA peak measured in this run)',
         },
     }
     if e2e is not None:
-        line['e2e'] = e2e
-    if world == 1 and args.workload == 'cfg2x256' and args.mode == 'sequential':
-        line['cfg2_single_chain'] = single_chain_probe(args, local_rank, stream)
+        line['e2e'] = e2e.pop('main')
+        line.update(e2e)                                  # e2e_keep1, e2e_chain_on_device
+    if cfg4 is not None:
+        line['cfg4_1gpu' if world == 1 else 'cfg4_tiled'] = cfg4
+    if world == 1 and args.workload == 'cfg2x256' and args.mode == 'sequential' and not args.no_probes:
+        # every other BASELINE.json configuration as a sub-record (CUDA events, state resident)
+        line['cfg2_single_chain'] = sweep_probe(args, local_rank, stream, 'cfg2', 1, 200, 50,
+                                                note='BASELINE configs[1] taken literally: ONE sequential-exact chain')
+        line['cfg1'] = sweep_probe(args, local_rank, stream, 'cfg1', 1, 100, 20,
+                                   note='configs[0]: bundled MUSE cube x1e20, MUSE() defaults, scalar variance, 1 chain')
+        line['cfg3_coloured'] = sweep_probe(args, local_rank, stream, 'cfg2x256', 256, 10, 2, mode='coloured',
+                                            note='configs[2]: colour-class updates, 256 chains')
+        line['cfg5'] = sweep_probe(args, local_rank, stream, 'cfg5', 512, 10, 2,
+                                   note='configs[4]: survey batch, 512 galaxies per GPU')
+        line['cfg2_fsf21'] = sweep_probe(args, local_rank, stream, 'cfg2_fsf21', 148, 5, 1,
+                                         note='cfg2 with the 21x21 stamp (SURVEY.md 8d secondary), 148 chains')
+        line['forward_microbench'] = forward_microbench(args, local_rank, stream, fp64_peak)
     if world == 1 and not args.no_cpu_baseline:
         cs = args.cpu_sweeps or 3
         n_procs = min(os.cpu_count() or 1, 8)
@@ -450,35 +506,158 @@ def main():
         dist.destroy_process_group()
 
 
-def single_chain_probe(args, local_rank, stream, sweeps=200):
-    """BASELINE.json configs[1] taken literally: ONE sequential-exact chain on the cfg2 cube (one
-    CTA on one SM, latency-bound, state resident in L2).  Reported next to the many-chain
-    headline so that both regimes of the metric are on the line; not part of the timed steps."""
+def sweep_probe(args, local_rank, stream, workload, chains, sweeps, warm, mode='sequential', note=None):
+    """One BASELINE.json configuration as a sub-record of the default line: set the problem up,
+    `warm` untimed sweeps, then `sweeps` sweeps timed with CUDA events on the library's stream.
+    Not part of the timed steps of the headline."""
     import torch
     from deconv3d_b200 import _native, rtnorm_tables
-    wl = build_workload('cfg2', 1)
-    arrays = realise(wl, 0)
-    ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_rtnorm_tables(*rtnorm_tables.tables())
-    ctx.set_rng(42, 0)
-    ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
-                    arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=1)
-    ctx.init_params_uniform()
-    ctx.forward(write_err=True)
-    ctx.sweep(1, 50, mode=_native.SEQ_EXACT, refresh_every=1000, min_acceptance_rate=0.0)
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    ctx.sweep(51, sweeps, mode=_native.SEQ_EXACT, refresh_every=1000, min_acceptance_rate=0.0)
-    e1.record(stream)
-    e1.synchronize()
-    ms = e0.elapsed_time(e1)
-    upd = ctx.counters()['last_sweep_site_updates']
-    ctx.close()
-    return {'value': upd / (ms * 1e-3), 'unit': UNIT, 'sweeps_per_s': sweeps / (ms * 1e-3),
-            'us_per_site_update': ms * 1e3 / upd, 'sweeps': sweeps, 'chains': 1,
-            'workload': wl['desc'], 'mode': 'sequential'}
+    try:
+        wl = build_workload(workload, chains)
+        arrays = realise(wl, 0)
+        ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_rtnorm_tables(*rtnorm_tables.tables())
+        ctx.set_rng(42, 0)
+        ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                        arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=wl['chains_per_cube'])
+        ctx.init_params_uniform()
+        ctx.forward(write_err=True)
+        nmode = _native.SEQ_EXACT if mode == 'sequential' else _native.COLOURED
+        ctx.sweep(1, warm, mode=nmode, refresh_every=1000, min_acceptance_rate=0.0)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.sweep(1 + warm, sweeps, mode=nmode, refresh_every=1000, min_acceptance_rate=0.0)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        c = ctx.counters()
+        upd = c['last_sweep_site_updates']
+        peak, _ = measured_peak()
+        ctx.close()
+        n_units = wl['n_cubes'] * wl['chains_per_cube']
+        rec = {'value': upd / (ms * 1e-3), 'unit': UNIT,
+               'sweeps_per_s': n_units * sweeps / (ms * 1e-3),
+               'us_per_site_update': ms * 1e3 / upd, 'sweeps': sweeps, 'units': n_units,
+               'workload': wl['desc'], 'mode': mode,
+               'nominal_hbm_frac': c['last_sweep_bytes'] / (ms * 1e-3) / 1e9 / peak}
+        if note:
+            rec['note'] = note
+        return rec
+    except Exception as e:                              # noqa: BLE001 - a probe never kills the line
+        return {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+
+
+def forward_microbench(args, local_rank, stream, fp64_peak_tflops, n=512):
+    """Forward model (lib/run.py:999-1031: spectral LSF pass + spatial FSF pass + residual) of a
+    survey batch of `n` cubes 32^3 for four FSF sizes: ms per call, fraction of the measured FP64
+    FMA peak (2 D H W fh fw flop of the FSF pass) and of the measured HBM peak (B_fwd = 4 s D H W:
+    lines written + read, data read, residual written)."""
+    import torch
+    from deconv3d_b200 import _native, MUSE
+    from deconv3d_b200.spread_functions import MoffatFieldSpreadFunction
+    out = []
+    peak, _ = measured_peak()
+    D = H = W = 32
+    rs = np.random.RandomState(0)
+    data = rs.rand(n, D, H, W)
+    var = np.full(data.shape, 0.01)
+    p = np.dstack([rs.rand(H, W) * 9, rs.rand(H, W) * (D - 1), 0.5 + rs.rand(H, W) * 3])
+    params = np.broadcast_to(p, (n, H, W, 3)).copy()
+    for fs in (3, 13, 21, 41):
+        try:
+            inst = MUSE(fsf=MoffatFieldSpreadFunction(fwhm=0.8, beta=2.5, size=fs))
+            cube0 = MUSE().build_cube(np.zeros((D, H, W)))
+            fsf = np.asarray(inst.fsf.as_image(cube0))
+            lsf = inst.lsf.as_vector(cube0)
+            ctx = _native.Context(local_rank, _native.F64)
+            ctx.set_stream(stream.cuda_stream)
+            ctx.set_problem(data, var, fsf, lsf, np.zeros((n, 3)), np.tile([100., D - 1, D], (n, 1)),
+                            [0, .1, .1], np.ones(n))
+            ctx.set_params(params)
+            for _ in range(2):
+                ctx.forward(write_err=True)
+            reps = 5
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                ctx.forward(write_err=True)
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            ctx.close()
+            vox = float(n) * D * H * W
+            out.append({'fsf': '%dx%d' % (fs, fs), 'ms': ms,
+                        'fp64_tflops': 2.0 * vox * fs * fs / ms / 1e9,
+                        'fp64_frac': 2.0 * vox * fs * fs / ms / 1e9 / fp64_peak_tflops,
+                        'hbm_gbs': 4 * 8 * vox / ms / 1e6, 'hbm_frac': 4 * 8 * vox / ms / 1e6 / peak})
+        except Exception as e:                          # noqa: BLE001
+            out.append({'fsf': '%dx%d' % (fs, fs), 'error': '%s: %s' % (type(e).__name__, str(e)[:200])})
+    return {'workload': 'forward model of %d cubes 32x32x32, f64, LSF sigma 0.9 px' % n, 'points': out,
+            'fp64_peak_tflops': fp64_peak_tflops, 'hbm_peak_gbs': peak}
+
+
+def tiled_probe(args, rank, local_rank, world, field=256, sweeps=1, warm=1):
+    """cfg4 as a sub-record: ONE cube field x field x 64 (FSF 41x41), 1 chain, coloured sweep; with
+    world > 1 the sites are tiled over the ranks and the outcome records of every colour phase
+    are exchanged over NVLink peer memory (strong scaling: the cube is fixed).  Every rank takes
+    part; the record is returned on every rank (max over ranks of the device time)."""
+    import torch
+    import torch.distributed as dist
+    from deconv3d_b200 import _native, rtnorm_tables
+    from deconv3d_b200 import dist as d3dist
+    try:
+        wl = build_workload('cfg4', field)
+        arrays = realise(wl, 0)                       # the same cube on every rank
+        D, H, W = wl['D'], wl['H'], wl['W']
+        fh, fw = arrays['fsf'].shape
+        ctx = _native.Context(local_rank, _native.F64 if args.dtype == 'f64' else _native.F32)
+        ctx.set_rtnorm_tables(*rtnorm_tables.tables())
+        ctx.set_rng(42, 0)
+        ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                        arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=1)
+        ctx.init_params_uniform()
+        ctx.forward(write_err=True)
+        if world == 1:
+            # one GPU: the library's own coloured sweep (one launch per colour class, C loop)
+            stream = torch.cuda.Stream(device=local_rank)
+            ctx.set_stream(stream.cuda_stream)
+            ctx.sweep(1, warm, mode=_native.COLOURED, refresh_every=0, min_acceptance_rate=0.0)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.sweep(1 + warm, sweeps, mode=_native.COLOURED, refresh_every=0, min_acceptance_rate=0.0)
+            e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            exchange = 'none (one GPU)'
+        else:
+            sw = d3dist.TiledSweeper([ctx], (H, W), (fh, fw), fused=args.exchange == 'fused')
+            stream = sw.stream
+            sw.sweep(1, warm, refresh_every=0)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sw.sweep(1 + warm, sweeps, refresh_every=0)
+            e1.record(stream)
+            e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            exchange = ('P2P stores of outcome records into every peer + flags (no collective)' if sw.fused
+                        else 'NCCL all-gather of outcome records per phase')
+            sw.finish()
+        ctx.close()
+        return {'value': float(H * W) * sweeps / (ms * 1e-3), 'unit': UNIT, 'ms_per_sweep': ms / sweeps,
+                'us_per_phase': ms * 1e3 / sweeps / (min(fh, H) * min(fw, W)), 'n_gpus': world,
+                'tiles': '%dx%d' % d3dist.tile_grid(H, W, world), 'exchange': exchange,
+                'scaling': 'strong', 'workload': wl['desc'], 'mode': 'coloured'}
+    except Exception as e:                              # noqa: BLE001
+        return {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
 
 
 def bench_tiled(args, rank, local_rank, world, sweeps):
@@ -586,49 +765,68 @@ def bench_tiled(args, rank, local_rank, world, sweeps):
 
 
 def run_e2e(args, wl, arrays, rank, local_rank, world, sweeps):
-    """Same metric through ``Run(...)``: numpy cube/variance in, chain rows out."""
+    """Same metric through ``Run(...)``: numpy cube/variance in, results out.  Three variants:
+    main                  keep_one_in = sweeps/2: two chain rows per chain come back
+    e2e_keep1             the reference's default keep_one_in = 1: EVERY row comes back (262 MB per
+                          step at the default workload)
+    e2e_chain_on_device   the chain stays in HBM, the posterior mean is reduced there
+                          (d3d_chain_mean); parameters + both output cubes come back"""
+    import logging
     import torch
     import torch.distributed as dist
     from deconv3d_b200 import Run, MUSE
     if wl['n_cubes'] != 1:
         return None
+    logging.getLogger('deconv3d').setLevel(logging.WARNING)
     cube = MUSE().build_cube(arrays['data'][0])
     var = arrays['var'][0] if wl['var_kind'] == 'cube' else None
     chains = wl['chains_per_cube']
-    keep = max(1, sweeps // 2)
-    kw = dict(variance=var, max_iterations=sweeps + 1, keep_one_in=keep, n_chains=chains,
-              seed=42, first_chain_id=rank * chains, device=local_rank,
-              mode=args.mode, dtype='float64' if args.dtype == 'f64' else 'float32',
-              min_acceptance_rate=0.0)
-    import logging
-    logging.getLogger('deconv3d').setLevel(logging.WARNING)
-    Run(cube, wl['inst'], **kw)                       # warm-up
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    # median of 5 calls: the host side of a shared box is noisy (page faults of the fresh chain
-    # arrays, other tenants), the device side is not
-    times = []
-    for _ in range(5):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run = Run(cube, wl['inst'], **kw)
-        torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    dt = float(np.median(times))
-    t = torch.tensor([dt], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    updates = sweeps * wl['H'] * wl['W'] * chains * world
     h2d = arrays['data'][0].nbytes + (var.nbytes if var is not None else 8) + arrays['fsf'].nbytes \
         + arrays['lsf'].nbytes
-    d2h = run.chains[:, 1:].nbytes + run.all_likelihoods[:, 1:].nbytes + run.chains[:, 0].nbytes
-    return {'value': updates / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-            'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
-            'ms_per_call_all': [round(t * 1e3, 1) for t in times],
-            'api': 'Run(cube, instrument, variance=..., max_iterations=%d, keep_one_in=%d, '
-                   'n_chains=%d)' % (sweeps + 1, keep, chains)}
+    updates = sweeps * wl['H'] * wl['W'] * chains * world
+
+    def one(keep, on_device, reps):
+        kw = dict(variance=var, max_iterations=sweeps + 1, keep_one_in=keep, n_chains=chains,
+                  seed=42, first_chain_id=rank * chains, device=local_rank,
+                  mode=args.mode, dtype='float64' if args.dtype == 'f64' else 'float32',
+                  min_acceptance_rate=0.0)
+        if on_device:
+            kw['chain_on_device'] = True
+        Run(cube, wl['inst'], **kw)                       # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        # median of `reps` calls: the host side of a shared box is noisy (page faults of the fresh
+        # chain arrays, other tenants), the device side is not
+        times = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run = Run(cube, wl['inst'], **kw)
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        dt = float(np.median(times))
+        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        if on_device:
+            d2h = run.parameters_all.nbytes + 2 * arrays['data'][0].nbytes   # posterior means + both output cubes
+        else:
+            d2h = run.chains[:, 1:].nbytes + run.all_likelihoods[:, 1:].nbytes + run.chains[:, 0].nbytes
+        return {'value': updates / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
+                'ms_per_call_all': [round(t * 1e3, 1) for t in times],
+                'api': 'Run(cube, instrument, variance=..., max_iterations=%d, keep_one_in=%d, '
+                       'n_chains=%d%s)' % (sweeps + 1, keep, chains, ', chain_on_device=True' if on_device else '')}
+
+    out = {'main': one(max(1, sweeps // 2), False, 5)}
+    for key, keep, dev in (('e2e_keep1', 1, False), ('e2e_chain_on_device', 1, True)):
+        try:
+            out[key] = one(keep, dev, 3)
+        except Exception as e:                          # noqa: BLE001
+            out[key] = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+    return out
 
 
 if __name__ == '__main__':

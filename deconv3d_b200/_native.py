@@ -27,6 +27,7 @@ SYMBOLS = [
     'd3d_set_tile', 'd3d_tile_record_slots', 'd3d_colour_begin', 'd3d_colour_phase',
     'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control', 'd3d_chain_mean',
     'd3d_tile_fused_init', 'd3d_tile_fused_export', 'd3d_tile_fused_connect', 'd3d_colour_phase_fused', 'd3d_sweep_fused',
+    'd3d_fp64_peak', 'd3d_last_kernel',
 ]
 RECORD_DOUBLES = 8
 ABI_VERSION = 2          # D3D_ABI_VERSION of include/deconv3d_b200.h
@@ -106,10 +107,13 @@ def load():
     lib.d3d_tile_fused_connect.argtypes = [vp, ci, vp, vp]
     lib.d3d_colour_phase_fused.argtypes = [vp, i64, ci, ci, i64]
     lib.d3d_sweep_fused.argtypes = [vp, i64, i64, cd]
+    lib.d3d_fp64_peak.argtypes = [vp, vp]
+    lib.d3d_last_kernel.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ('d3d_last_error',):
+        if name not in ('d3d_last_error', 'd3d_last_kernel'):
             fn.restype = ci
+    lib.d3d_last_kernel.restype = ctypes.c_char_p
     if lib.d3d_abi_version() != ABI_VERSION:
         raise NativeError(EINVAL, 'libdeconv3d_b200.so has ABI %d, expected %d'
                           % (lib.d3d_abi_version(), ABI_VERSION))
@@ -365,6 +369,16 @@ class Context(object):
         out = np.empty((self.n_chains, H, W, 3))
         _check(self.lib.d3d_chain_mean(self.h, _ptr(chain), int(chain.shape[1]), int(first_row), _ptr(out)))
         return out
+
+    def last_kernel(self):
+        """Name of the sweep kernel the latest sweep() launched."""
+        return self.lib.d3d_last_kernel(self.h).decode()
+
+    def fp64_peak(self):
+        """Measured FP64 FMA peak of the device in TFLOP/s (bench support)."""
+        v = ctypes.c_double(0.0)
+        _check(self.lib.d3d_fp64_peak(self.h, ctypes.byref(v)))
+        return v.value
 
     def counters(self):
         a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)

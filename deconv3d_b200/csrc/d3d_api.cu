@@ -22,6 +22,24 @@
 
 using namespace d3d;
 
+// pipelined sweep kernel (d3d_pipe.cuh): look-ahead, producer warps and thread bound of the
+// instantiation that ships; -D overrides are for the A/B builds of profiles/tools
+#ifndef D3D_PIPE_L
+#define D3D_PIPE_L 2
+#endif
+#ifndef D3D_PIPE_NA
+#define D3D_PIPE_NA 3
+#endif
+#ifndef D3D_PIPE_NP
+#define D3D_PIPE_NP 3
+#endif
+#ifndef D3D_PIPE_NX
+#define D3D_PIPE_NX 2
+#endif
+#ifndef D3D_PIPE_MAXT
+#define D3D_PIPE_MAXT 640
+#endif
+
 static thread_local std::string g_last_error;
 
 static int fail(int code, const char* fmt, ...) {
@@ -141,6 +159,9 @@ struct d3d_ctx {
     int generic_threads = 256;
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
     static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
+    // pipelined sweep kernel (d3d_pipe.cuh): look-ahead L, producer warps, launch shape
+    bool use_pipe = false; int pipe_L = 2, pipe_NA = 3, pipe_NP = 3, pipe_threads = 0; size_t pipe_smem = 0;
+    int* d_sites_row = nullptr; int* d_run_start = nullptr; double mean_run = 0.0;
     void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
     long long sched_C = -1, sched_S = -1; int sched_G = -1, sched_max_items = 1; size_t sched_flat = 0;
     bool use_nc = false;                // uncached row kernel (2 CTAs/SM) for many chains
@@ -155,6 +176,7 @@ struct d3d_ctx {
     double* d_rec_stage = nullptr; size_t rec_stage_cap = 0;   // staging of host-side record buffers
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
+    const char* last_kernel = "";        // name of the sweep kernel of the latest d3d_sweep (bench reporting)
     int64_t window_voxels_per_sweep = 0;   // sum over cubes of sum_sites wh*ww*D * chains_per_cube
     std::vector<int> h_nsites;
     size_t elem() const { return dtype == D3D_F64 ? 8 : 4; }
@@ -176,6 +198,10 @@ static void free_problem(d3d_ctx* c) {
     c->allocs.clear();
     c->d_lines = nullptr;
     c->pb.gtab = nullptr;
+    c->pb.xtab = nullptr;
+    c->pb.run_start = nullptr;
+    c->pb.run_last = nullptr;
+    c->d_sites_row = nullptr; c->d_run_start = nullptr;
     c->have_problem = false;
     c->have_params = false;
 }
@@ -289,6 +315,20 @@ static void choose_launch(d3d_ctx* c) {
         c->use_slide = c->ne != 0 && c->ne <= 13 && c->slide_threads <= 384 && pb.W >= 2 &&
                        (long long)pb.H * pb.W * pb.W < 0xffffffffLL;   // multiply-high site decode
         if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
+        // pipelined variant: fw + L + 1 column groups + producer / cross-term / decision warps
+        {
+            c->pipe_L = D3D_PIPE_L; c->pipe_NA = D3D_PIPE_NA; c->pipe_NP = D3D_PIPE_NP;
+            const int ng = pb.fw + c->pipe_L + 1;
+            const int nww = (ng * zl + 31) / 32;
+            c->pipe_threads = (nww + c->pipe_NA + c->pipe_NP + D3D_PIPE_NX + PIPE_NR + 1) * 32;   // (+ reducer) + decision warp
+            c->pipe_smem = pipe_smem_bytes<D3D_PIPE_L>(pb.fw, c->ne ? c->ne : 7, pb.kd_n, pb.Dp,
+                                                       c->pipe_NA + c->pipe_NP, ng, zl, pb.var_is_cube != 0);
+            // needs runs to pipeline along; Dp <= 64: one producer lane per channel pair, the cross
+            // terms of a site in two registers per lane; <= 16 window warps: one record row
+            c->use_pipe = c->use_slide && c->pipe_threads <= D3D_PIPE_MAXT && c->pipe_smem <= 227 * 1024 &&
+                          nww <= 16 && pb.Dp <= 64 && c->mean_run >= 4.0;
+            if (const char* e = getenv("D3D_PIPE")) c->use_pipe = c->use_pipe && atoi(e) != 0;
+        }
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
     c->colour_attr_set = false;
@@ -419,9 +459,43 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     c->window_voxels_per_sweep = wvox;
     c->h_nsites = nsites;
     pb.max_sites = max_sites;
+    // runs of the row-major list: consecutive entries on one row with x increasing by one
+    // (d3d_pipe.cuh pipelines the decisions inside a run and drains at its end)
+    std::vector<int> runs((size_t)n_cubes * max_sites, 0);
+    {
+        long long n_runs = 0, n_all = 0;
+        for (int q = 0; q < n_cubes; ++q) {
+            const int* sl = sites.data() + (size_t)q * max_sites;
+            int* rl = runs.data() + (size_t)q * max_sites;
+            for (int k = 0; k < nsites[q]; ++k) {
+                const bool cont = k > 0 && sl[k] == sl[k - 1] + 1 && sl[k] % W != 0;
+                rl[k] = cont ? rl[k - 1] : k;
+                n_runs += !cont;
+            }
+            n_all += nsites[q];
+        }
+        c->mean_run = n_runs ? (double)n_all / (double)n_runs : 0.0;
+    }
+    std::vector<int> runl((size_t)n_cubes * max_sites, 0);
+    for (int q = 0; q < n_cubes; ++q) {
+        const int* rl = runs.data() + (size_t)q * max_sites;
+        int* ll = runl.data() + (size_t)q * max_sites;
+        for (int k = nsites[q] - 1; k >= 0; --k)
+            ll[k] = (k + 1 < nsites[q] && rl[k + 1] == rl[k]) ? ll[k + 1] : k;
+    }
     uint8_t* d_mask; int* d_sites; int* d_ns;
     if ((rc = dalloc(c, &d_mask, hmask.size()))) return rc;
     if ((rc = dalloc(c, &d_sites, sites.size() * sizeof(int)))) return rc;
+    if ((rc = dalloc(c, &c->d_run_start, runs.size() * sizeof(int)))) return rc;
+    CK(cudaMemcpy(c->d_run_start, runs.data(), runs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->d_sites_row = d_sites;
+    pb.run_start = c->d_run_start;
+    {
+        int* d_rl;
+        if ((rc = dalloc(c, &d_rl, runl.size() * sizeof(int)))) return rc;
+        CK(cudaMemcpy(d_rl, runl.data(), runl.size() * sizeof(int), cudaMemcpyHostToDevice));
+        pb.run_last = d_rl;
+    }
     if ((rc = dalloc(c, &c->d_sites_colour, csites.size() * sizeof(int)))) return rc;
     CK(cudaMemcpy(c->d_sites_colour, csites.data(), csites.size() * sizeof(int), cudaMemcpyHostToDevice));
     if ((rc = dalloc(c, &d_ns, n_cubes * sizeof(int)))) return rc;
@@ -457,6 +531,20 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
             if (hk[m] != 0.0 && fabs(hk[m]) >= 1e-18 * kmax) { tapv.push_back(hk[m]); tapm.push_back(m); }
     }
     pb.ntaps = (int)tapv.size();
+    // the same taps as ONE dense window of signed offsets m' in [mlo, mhi] (m' = m or m - P):
+    // kdense[t] = K[(mhi - t) mod P]; out[z] = sum_t kdense[t] * g[(z - mhi + t) mod P]
+    std::vector<double> kdense;
+    {
+        int mlo = 0, mhi = 0; bool any = false;
+        for (int m : tapm) {
+            const int ms = m < pb.P / 2 ? m : m - pb.P;
+            if (!any) { mlo = mhi = ms; any = true; }
+            mlo = std::min(mlo, ms); mhi = std::max(mhi, ms);
+        }
+        if (!any) { mlo = mhi = 0; }
+        for (int t = 0; t <= mhi - mlo; ++t) kdense.push_back(hk[((mhi - t) % pb.P + pb.P) % pb.P]);
+        pb.kd_n = (int)kdense.size(); pb.kd_mhi = mhi;
+    }
     // runs of consecutive tap offsets (lines_warp_kernel rotates its buffer inside a run)
     c->tap_runs = tapm.empty() ? 0 : 1;
     c->tap_run2 = (int)tapm.size();
@@ -472,6 +560,12 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
         CK(cudaMemcpy(d_tm, tapm.data(), tapm.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     pb.ktap_v = d_tv; pb.ktap_m = d_tm;
+    {
+        double* d_kd;
+        if ((rc = dalloc(c, &d_kd, kdense.size() * sizeof(double)))) return rc;
+        CK(cudaMemcpy(d_kd, kdense.data(), kdense.size() * sizeof(double), cudaMemcpyHostToDevice));
+        pb.kdense = d_kd;
+    }
     CK(cudaMemcpy(d_fsf, hfsf.data(), hfsf.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_k, hk.data(), hk.size() * sizeof(double), cudaMemcpyHostToDevice));
     pb.fsf = d_fsf; pb.kcirc = d_k;
@@ -492,11 +586,11 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     if ((rc = dalloc(c, &d_it, pb.n_chains * sizeof(long long)))) return rc;
     if ((rc = dalloc(c, &d_rate, pb.n_chains * sizeof(double)))) return rc;
     if ((rc = dalloc(c, &d_active, pb.n_chains * sizeof(int)))) return rc;
-    if ((rc = dalloc(c, &d_status, sizeof(int)))) return rc;
+    if ((rc = dalloc(c, &d_status, 33 * sizeof(int)))) return rc;
     CK(cudaMemset(d_params, 0, (size_t)pb.n_chains * HW * 3 * sizeof(double)));
-    CK(cudaMemset(d_status, 0, sizeof(int)));
+    CK(cudaMemset(d_status, 0, 33 * sizeof(int)));
     pb.params = d_params; pb.accepted = d_acc; pb.iters = d_it; pb.rate = d_rate;
-    pb.active = d_active; pb.status = d_status;
+    pb.active = d_active; pb.status = d_status; pb.dbg = d_status + 1;
     pb.ty0 = 0; pb.ty1 = H; pb.tx0 = 0; pb.tx1 = W;
     pb.ry0 = 0; pb.ry1 = H; pb.rx0 = 0; pb.rx1 = W;
     pb.lik_cur = nullptr; pb.acc_cur = nullptr;              // allocated by d3d_set_tile
@@ -917,6 +1011,7 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
                               long long rows_local) {
     if (NE != 0 && c->use_slide) {
         const int ne = NE ? NE : 7;
+        const int nes = ne > 13 ? 13 : ne;
         if (!c->pb.gtab) {                                      // static G table, once per problem
             double* g = nullptr;
             const size_t n = (size_t)c->pb.n_cubes * c->pb.H * c->pb.W;
@@ -925,8 +1020,42 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             c->launches++;
             c->pb.gtab = g;
         }
-        cudaFuncSetAttribute(sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->slide_smem);
+        // the pipelined kernel walks the ROW-MAJOR list (runs of consecutive sites); the
+        // colour-ordered list of the chain-per-CTA coloured mode has no runs: sliding-window kernel
+        // Measured (profiles/r02_notes.md): the pipelined kernel is 1.4x faster per chain while
+        // the chip is partly filled (0.50 M vs 0.36 M evals/s for one chain), but its larger
+        // per-site instruction footprint costs more than the pipelining gains once every SM runs
+        // a chain (42 M vs 52 M evals/s at 148+ chains): it takes the launches of up to 3/4 SMs.
+        int sms_ = 148;
+        cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, c->device);
+        bool few = c->pb.n_chains <= (3 * sms_) / 4;
+        if (const char* e = getenv("D3D_PIPE")) few = atoi(e) >= 2 ? true : few;   // D3D_PIPE=2: always
+        const bool pipe = c->use_pipe && few && c->pb.sites == c->d_sites_row;
+        if (pipe && !c->pb.xtab) {                              // static cross-term tables, once per problem
+            double* xt = nullptr;
+            const size_t n = (size_t)c->pb.n_cubes * c->pipe_L * c->pb.max_sites * c->pb.Dp;
+            if (dalloc(c, &xt, n * sizeof(double))) return cudaErrorMemoryAllocation;
+            dim3 grid(c->pb.max_sites, c->pipe_L, c->pb.n_cubes);
+            xtab_kernel<T, IV><<<grid, 64, 0, c->stream>>>(c->pb, c->pipe_L, c->d_run_start, xt);
+            c->launches++;
+            c->pb.xtab = xt;
+        }
+        typedef void (*SeqKern)(const Problem, long long, long long, int, double, double*, double*,
+                                long long, long long, const int4*, const int*, int, volatile long long*);
+        SeqKern kern = sweep_seq_slide_kernel<T, IV, nes>;
+        int threads = c->slide_threads;
+        size_t smem = c->slide_smem;
+        c->last_kernel = pipe ? "sweep_seq_pipe_kernel" : "sweep_seq_slide_kernel";
+        if (pipe) {
+            // (square FSF of the template's size: the window geometry is a compile-time constant)
+            if (c->pb.fh == nes && c->pb.fw == nes)
+                kern = sweep_seq_pipe_kernel<T, IV, nes, true, D3D_PIPE_L, D3D_PIPE_NA, D3D_PIPE_NP, D3D_PIPE_NX, D3D_PIPE_MAXT>;
+            else
+                kern = sweep_seq_pipe_kernel<T, IV, nes, false, D3D_PIPE_L, D3D_PIPE_NA, D3D_PIPE_NP, D3D_PIPE_NX, D3D_PIPE_MAXT>;
+            threads = c->pipe_threads;
+            smem = c->pipe_smem;
+        }
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // balance chains over the SMs (McNaughton wrap-around of the chain x sweep rectangle)
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -985,26 +1114,27 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             int* d_cnt = (int*)(base + c->sched_flat * sizeof(int4) + C * sizeof(long long));
             fill_ll_kernel<<<(C + 255) / 256, 256, 0, c->stream>>>(d_prog, C, it0);
             c->launches++;
-            sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<G, c->slide_threads, c->slide_smem, c->stream>>>(
-                c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local,
-                d_items, d_cnt, max_items, d_prog);
+            kern<<<G, threads, smem, c->stream>>>(c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev,
+                                                  row_first, rows_local, d_items, d_cnt, max_items, d_prog);
         } else {
-            sweep_seq_slide_kernel<T, IV, (ne > 13 ? 13 : ne)><<<C, c->slide_threads, c->slide_smem, c->stream>>>(
-                c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local,
-                nullptr, nullptr, 0, nullptr);
+            kern<<<C, threads, smem, c->stream>>>(c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev,
+                                                  row_first, rows_local, nullptr, nullptr, 0, nullptr);
         }
     } else if (NE != 0 && c->use_nc) {
+        c->last_kernel = "sweep_seq_nc_kernel";
         cudaFuncSetAttribute(sweep_seq_nc_kernel<T, IV>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         sweep_seq_nc_kernel<T, IV><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
             c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
     } else if (NE == 0) {
+        c->last_kernel = "sweep_seq_generic_kernel";
         cudaFuncSetAttribute(sweep_seq_generic_kernel<T, IV>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         sweep_seq_generic_kernel<T, IV><<<c->pb.n_chains, c->generic_threads, c->sweep_smem, c->stream>>>(
             c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
     } else {
         const int ne = NE ? NE : 7;    // (never instantiates the row kernel with 0 rows)
+        c->last_kernel = "sweep_seq_kernel";
         cudaFuncSetAttribute(sweep_seq_kernel<T, IV, ne>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         sweep_seq_kernel<T, IV, ne><<<c->pb.n_chains, c->threads, c->sweep_smem, c->stream>>>(
@@ -1030,6 +1160,8 @@ static cudaError_t launch_colour_class(d3d_ctx* c, long long it, int cy, int cx,
     }
     const int nly = (pb.H + pb.fh - 1) / pb.fh, nlx = (pb.W + pb.fw - 1) / pb.fw;
     dim3 grid(nly * nlx, pb.n_chains);
+    c->last_kernel = NE == 0 ? (c->cluster ? "sweep_colour_cluster_kernel" : "sweep_colour_generic_kernel")
+                             : "sweep_colour_kernel";
     if (NE == 0 && c->cluster) {
         if (!c->cluster_attr_set) {
             cudaFuncSetAttribute(sweep_colour_cluster_kernel<T, IV>,
@@ -1223,6 +1355,16 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
     c->last_updates = updates;
     c->last_bytes = (int64_t)((pb.var_is_cube ? 3 : 2) * (double)c->elem() *
                               (double)c->window_voxels_per_sweep * (double)n_iterations);
+    if (h_status & 0x40000000) {
+        int prog[32] = {0};
+        cudaMemcpy(prog, pb.dbg, sizeof prog, cudaMemcpyDeviceToHost);
+        char buf[400]; int o = 0;
+        for (int q = 0; q < 24; ++q) o += snprintf(buf + o, sizeof buf - o, " %d", prog[q]);
+        return fail(D3D_ECUDA, "the pipelined sweep kernel stalled on an internal barrier (wait code %d at list "
+                               "entry %d; list index reached by warp:%s) and gave up; results of this call are "
+                               "invalid (D3D_PIPE=0 selects the sliding-window kernel)", h_status & 0xff,
+                    (h_status & 0x3fffffff) >> 8, buf);
+    }
     if (h_status)
         return fail(D3D_ENUMERIC, "cannot convert float NaN to integer: a NaN reached the truncated-normal sampler "
                                   "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");
@@ -1233,6 +1375,15 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
 extern "C" int d3d_debug_trace2(unsigned long long* out) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out, d3d::g_tr2, 16 * 16 * 16 * sizeof(unsigned long long));
+    return 0;
+}
+#endif
+
+#ifdef D3D_PIPE_PROF
+extern "C" int d3d_debug_pipe_prof(unsigned long long* out512, int reset) {
+    cudaDeviceSynchronize();
+    if (out512) cudaMemcpyFromSymbol(out512, d3d::g_pipe_prof, 32 * 16 * sizeof(unsigned long long));
+    if (reset) { static unsigned long long z[32 * 16]; cudaMemcpyToSymbol(d3d::g_pipe_prof, z, sizeof z); }
     return 0;
 }
 #endif
@@ -1548,6 +1699,16 @@ extern "C" int d3d_get_chain_control(d3d_ctx* c, int64_t* accepted_out, int64_t*
     CK(cudaMemcpy(&h_status, pb.status, sizeof(int), cudaMemcpyDeviceToHost));
     if (h_status == 2)
         return fail(D3D_ECUDA, "tile exchange timed out: a peer never published its colour phase");
+    if (h_status & 0x40000000) {
+        int prog[32] = {0};
+        cudaMemcpy(prog, pb.dbg, sizeof prog, cudaMemcpyDeviceToHost);
+        char buf[400]; int o = 0;
+        for (int q = 0; q < 24; ++q) o += snprintf(buf + o, sizeof buf - o, " %d", prog[q]);
+        return fail(D3D_ECUDA, "the pipelined sweep kernel stalled on an internal barrier (wait code %d at list "
+                               "entry %d; list index reached by warp:%s) and gave up; results of this call are "
+                               "invalid (D3D_PIPE=0 selects the sliding-window kernel)", h_status & 0xff,
+                    (h_status & 0x3fffffff) >> 8, buf);
+    }
     if (h_status)
         return fail(D3D_ENUMERIC, "cannot convert float NaN to integer: a NaN reached the truncated-normal sampler "
                                   "(lib/rtnorm.py:144) or a rejection loop exceeded its guard");
@@ -1586,6 +1747,46 @@ extern "C" int d3d_chain_mean(d3d_ctx* c, const double* chain, int64_t n_rows, i
     if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_chain_mean failed: %s", cudaGetErrorString(e));
     return 0;
 }
+
+__global__ void __launch_bounds__(1024) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int d3d_fp64_peak(d3d_ctx* c, double* tflops_out) {
+    if (!c || !tflops_out) return fail(D3D_EINVAL, "d3d_fp64_peak: NULL argument");
+    CK(cudaSetDevice(c->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int blocks = sms * 2, threads = 1024, iters = 2048;
+    double* out = nullptr;
+    CK(dev_malloc(&out, sizeof(double) * blocks * threads));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(c->ev0, c->stream);
+        dfma_peak_kernel<<<blocks, threads, 0, c->stream>>>(out, iters, 0.999999, 1e-6);
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (rep && ms < best) best = ms;
+        c->launches++;
+    }
+    dev_free(out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(D3D_ECUDA, "d3d_fp64_peak failed: %s", cudaGetErrorString(e));
+    *tflops_out = 2.0 * 64.0 * iters * (double)blocks * threads / best / 1e9;
+    return 0;
+}
+
+extern "C" const char* d3d_last_kernel(d3d_ctx* c) { return c ? c->last_kernel : ""; }
 
 extern "C" int d3d_get_counters(d3d_ctx* c, int64_t* kernel_launches, int64_t* last_sweep_bytes,
                                 int64_t* last_sweep_site_updates) {

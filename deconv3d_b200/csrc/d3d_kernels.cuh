@@ -50,10 +50,15 @@ struct Problem {
     const int* n_sites;        // [cube]
     const double* fsf;         // [fh*fw]
     const double* gtab;        // [cube][H*W][Dp] sum of F^2/sigma^2 over the window of a site (d3d_slide.cuh), or NULL
+    const int* run_start;      // [cube][max_sites] index of the first site of the run a list entry belongs to (d3d_pipe.cuh), or NULL
+    const int* run_last;       // [cube][max_sites] index of the last site of that run, or NULL
+    const double* xtab;        // [cube][L][max_sites][Dp] cross terms of consecutive sites (d3d_pipe.cuh), or NULL
     const double* kcirc;       // [P] circular LSF kernel (lib/convolution.py:89-160 in direct form)
     const double* ktap_v;      // [ntaps] values and
     const int* ktap_m;         // [ntaps] offsets m of the taps with |K[m]| >= 1e-18 max|K|
     int ntaps;
+    const double* kdense;      // [kd_n] the same kernel as a dense window of signed offsets mhi, mhi-1, ... (d3d_pipe.cuh)
+    int kd_n, kd_mhi;
     const double* pmin;        // [cube][3]
     const double* pmax;        // [cube][3]
     const double* prior_var;   // [cube]
@@ -66,6 +71,7 @@ struct Problem {
     double* rate;              // [chain]  cur_acceptance_rate      (lib/run.py:356-359)
     int* active;               // [chain]
     int* status;               // [1] sticky numeric-failure flag
+    int* dbg;                  // [32] per-warp progress of the pipelined sweep kernel when it gives up
     // Spatial tiling of ONE cube over several contexts/GPUs (coloured mode, d3d_tile.cuh):
     // only sites inside the tile are updated by this context; the residual is kept valid
     // inside the region = tile grown by the FSF half-size.
@@ -1413,5 +1419,6 @@ __global__ void conv1d_kernel(const double* lines, const double* kcirc, double* 
 }  // namespace d3d
 
 #include "d3d_slide.cuh"
+#include "d3d_pipe.cuh"
 #include "d3d_stencil.cuh"
 #include "d3d_tile.cuh"

@@ -53,6 +53,21 @@ __device__ __forceinline__ void philox_block_inl(uint32_t k0, uint32_t k1, uint3
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+// Rolled form (code footprint of the pipelined sweep kernel, d3d_pipe.cuh): same rounds.
+__device__ __forceinline__ void philox_block_rolled(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
+                                                    uint32_t c2, uint32_t c3, uint32_t* o) {
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+        uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
 struct Philox {
     uint32_t k0, k1;          // key
     uint32_t site, sweep, chain;

@@ -246,6 +246,15 @@ int d3d_chain_mean(d3d_ctx* ctx, const double* chain, int64_t n_rows, int64_t fi
 int d3d_get_counters(d3d_ctx* ctx, int64_t* kernel_launches,
                      int64_t* last_sweep_bytes, int64_t* last_sweep_site_updates);
 
+/* Bench support: measured FP64 FMA peak of the context's device in TFLOP/s (8 independent
+ * DFMA chains per thread, every SM full, best of 5) -- the denominator of the FP64-pipe
+ * fractions bench.py reports for the forward-model stencil and the sweep kernel.  Nothing in
+ * the reference corresponds to it (the reference has no device code). */
+int d3d_fp64_peak(d3d_ctx* ctx, double* tflops_out);
+
+/* Bench support: name of the sweep kernel the latest d3d_sweep launched (static string). */
+const char* d3d_last_kernel(d3d_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,8 +68,27 @@ def _check_chain(ref, trace, chain, lik, acc, its, residual, data, keep=1, rtol=
             ok[it // keep, y, x, 0] = False
     assert (~ok).sum() <= 0.005 * ok.size
     sel = ok & m[None, :, :, None]
-    np.testing.assert_allclose(chain[sel], ref['chain'][sel], rtol=rtol, atol=1e-12 * scale)
-    np.testing.assert_allclose(lik[1:, m], ref['likelihoods'][1:, m], rtol=max(rtol, 1e-6), atol=1e-9)
+    # chains to 1e-9 relative.  Right after a random start the window sums are ~1e9 and cancel
+    # down to the posterior mean, so the amplitude carries their rounding: on top of rtol the Gibbs
+    # draw may deviate by 1e-7 of its own posterior standard deviation sqrt(ro) (lib/run.py:492-496)
+    atol = np.full(ref['chain'].shape, 1e-12 * scale)
+    for (it, y, x), v in trace.items():
+        if it % keep == 0:
+            atol[it // keep, y, x, 0] += 1e-7 * np.sqrt(abs(v[6]))
+    dev = np.abs(chain - ref['chain'])
+    bad = sel & (dev > rtol * np.abs(ref['chain']) + atol)
+    assert not bad.any(), (np.argwhere(bad)[:5], dev[bad][:5], ref['chain'][bad][:5])
+    # delta-logL to 1e-6 relative; the REFERENCE forms it as the difference of two O(N) sums
+    # (lib/run.py:423-426), so its own value carries ~eps * ar_old of cancellation noise (ar_old is
+    # ~5e8 right after a random start): that noise is allowed on top, element by element
+    ar_old = np.zeros(lik.shape)
+    for (it, y, x), v in trace.items():
+        if it % keep == 0:
+            ar_old[it // keep, y, x] = abs(v[1])
+    d_dev, d_ref = lik[1:, m], ref['likelihoods'][1:, m]
+    tol = max(rtol, 1e-6) * np.abs(d_ref) + 1e-9 + 1e-14 * ar_old[1:, m]
+    bad = np.abs(d_dev - d_ref) > tol
+    assert not bad.any(), (np.abs(d_dev - d_ref)[bad][:5], d_ref[bad][:5], ar_old[1:, m][bad][:5])
     if residual is not None:
         np.testing.assert_allclose(residual, ref['err'], rtol=0, atol=1e-9 * np.abs(data).max())
 
@@ -111,9 +130,13 @@ def _device_run(nat, arrays, chains_per_cube, max_it, mode, seed=42, first_chain
     return chain, lik, acc, its, res
 
 
-def test_cfg2x256_benched_launch_vs_oracle(nat):
-    """(i) The headline workload itself: 256 chains, balanced (wrap-around) launch of the
-    sliding-window kernel <double, variance cube, 13 rows>, row-major order."""
+@pytest.mark.parametrize('pipe', ['1', '2'])
+def test_cfg2x256_benched_launch_vs_oracle(nat, monkeypatch, pipe):
+    """(i) The headline workload itself: 256 chains, balanced (wrap-around) launch, row-major
+    order, <double, variance cube, 13 rows>: with the kernel the library picks at this chain
+    count (D3D_PIPE=1: sliding-window kernel) and with the pipelined kernel forced onto the same
+    balanced launch (D3D_PIPE=2: its work-item / hand-over path)."""
+    monkeypatch.setenv('D3D_PIPE', pipe)
     wl, arrays = _bench_arrays('cfg2x256', 256)
     max_it = 4
     chain, lik, acc, its, res = _device_run(nat, arrays, 256, max_it, nat.SEQ_EXACT)
@@ -194,12 +217,16 @@ def test_depth64_vs_oracle(nat, fsf_size):
     _check_chain(ref, trace, chain[k], lik[k], int(acc[k]), int(its[k]), res[k], data)
 
 
-def test_balanced_schedule_with_stopped_chains(nat):
-    """More chains than SMs, min_acceptance_rate > 0 and chains that stop early, followed by a
+@pytest.mark.parametrize('pipe', ['0', '2'])
+def test_balanced_schedule_with_stopped_chains(nat, monkeypatch, pipe):
+    """(both sweep kernels, one at a time -- D3D_PIPE=0: sliding-window kernel everywhere, D3D_PIPE=2:
+    pipelined kernel everywhere, also on the balanced launch; bit equality holds per kernel)
+    More chains than SMs, min_acceptance_rate > 0 and chains that stop early, followed by a
     second d3d_sweep call: a CTA whose FIRST work item is a stopped chain must still serve its
     remaining chains correctly (the truncated-normal tables are loaded once per CTA, not inside
     the first item).  Every chain equals its own single-chain run."""
     from conftest import load_golden
+    monkeypatch.setenv('D3D_PIPE', pipe)
     g = load_golden('ref_run_A')
     data, fsf, lsf = g['data'], g['fsf'], g['lsf']
     from oracle import reference_port as port

@@ -119,10 +119,12 @@ def test_fused_peer_memory_exchange_equals_one_context(nat, case):
         np.testing.assert_allclose(r, res1, rtol=0, atol=1e-9)
 
 
-def test_fused_exchange_gives_up_on_a_silent_peer(nat):
+def test_fused_exchange_gives_up_on_a_silent_peer(nat, monkeypatch):
     """A peer that never publishes its phase must not hang the GPU: the applier's wait is bounded
-    (~2 s), later phases give up at once, and the error surfaces through the C ABI."""
+    (D3D_TILE_TIMEOUT_S, 30 s by default; 2 s here), later phases give up at once, and the error
+    surfaces through the C ABI."""
     import time
+    monkeypatch.setenv('D3D_TILE_TIMEOUT_S', '2')
     prob = _problem(8, 12, 14, (5, 5), 2)
     data, var, fsf, lsf, mask, init = prob
     ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, mask=mask, seed=3)
