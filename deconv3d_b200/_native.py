@@ -27,7 +27,7 @@ SYMBOLS = [
     'd3d_set_tile', 'd3d_tile_record_slots', 'd3d_colour_begin', 'd3d_colour_phase',
     'd3d_apply_records', 'd3d_get_likelihoods', 'd3d_get_chain_control', 'd3d_chain_mean',
     'd3d_tile_fused_init', 'd3d_tile_fused_export', 'd3d_tile_fused_connect', 'd3d_colour_phase_fused', 'd3d_sweep_fused',
-    'd3d_fp64_peak', 'd3d_last_kernel',
+    'd3d_fp64_peak', 'd3d_last_kernel', 'd3d_set_line_model',
 ]
 RECORD_DOUBLES = 8
 ABI_VERSION = 2          # D3D_ABI_VERSION of include/deconv3d_b200.h
@@ -108,6 +108,7 @@ def load():
     lib.d3d_colour_phase_fused.argtypes = [vp, i64, ci, ci, i64]
     lib.d3d_sweep_fused.argtypes = [vp, i64, i64, cd]
     lib.d3d_fp64_peak.argtypes = [vp, vp]
+    lib.d3d_set_line_model.argtypes = [vp, ci, vp, vp]
     lib.d3d_last_kernel.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -369,6 +370,15 @@ class Context(object):
         out = np.empty((self.n_chains, H, W, 3))
         _check(self.lib.d3d_chain_mean(self.h, _ptr(chain), int(chain.shape[1]), int(first_row), _ptr(out)))
         return out
+
+    def set_line_model(self, offsets=None, ratios=None):
+        """Tied multiplet of Gaussians (offsets in channels, relative amplitudes); None: one Gaussian."""
+        if offsets is None:
+            _check(self.lib.d3d_set_line_model(self.h, 1, None, None))
+            return
+        off, rat = _f64(offsets).ravel(), _f64(ratios).ravel()
+        assert off.shape == rat.shape
+        _check(self.lib.d3d_set_line_model(self.h, int(off.size), _ptr(off), _ptr(rat)))
 
     def last_kernel(self):
         """Name of the sweep kernel the latest sweep() launched."""

@@ -367,6 +367,7 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
     unsigned int keep_first = pb.first_chain;
     memset(&pb, 0, sizeof pb);
     pb.rt = keep_rt; pb.seed = keep_seed; pb.first_chain = keep_first;
+    pb.n_comp = 1; pb.comp_ratio[0] = 1.0;                  // SingleGaussianLineModel until d3d_set_line_model
     const int vec = c->dtype == D3D_F64 ? 2 : 4;
     pb.D = D; pb.H = H; pb.W = W; pb.Dp = ((D + vec - 1) / vec) * vec;
     pb.fh = fh; pb.fw = fw; pb.fhh = (fh - 1) / 2; pb.fhw = (fw - 1) / 2;
@@ -613,6 +614,29 @@ static int reset_chain_control(d3d_ctx* c) {
     CK(cudaMemcpyAsync(pb.rate, rate.data(), rate.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(pb.active, act.data(), act.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int d3d_set_line_model(d3d_ctx* c, int n_components, const double* offsets, const double* ratios) {
+    if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_set_line_model before d3d_set_problem");
+    if (n_components < 1 || n_components > 4)
+        return fail(D3D_EINVAL, "d3d_set_line_model: 1 to 4 tied Gaussian components are supported");
+    if (n_components > 1 && (!offsets || !ratios)) return fail(D3D_EINVAL, "d3d_set_line_model: NULL argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    Problem& pb = c->pb;
+    double off[4] = {0, 0, 0, 0}, rat[4] = {1, 0, 0, 0};
+    if (n_components > 1) {
+        CK(cudaMemcpy(off, offsets, n_components * sizeof(double), cudaMemcpyDefault));
+        CK(cudaMemcpy(rat, ratios, n_components * sizeof(double), cudaMemcpyDefault));
+    }
+    if (!(rat[0] != 0.0)) return fail(D3D_EINVAL, "d3d_set_line_model: the first component carries the amplitude, its ratio must not be 0");
+    // normalised to the first component: offset 0, ratio 1 (the amplitude parameter is ITS amplitude)
+    pb.n_comp = n_components;
+    for (int k = 0; k < 4; ++k) {
+        pb.comp_off[k] = k < n_components ? off[k] - off[0] : 0.0;
+        pb.comp_ratio[k] = k < n_components ? rat[k] / rat[0] : 0.0;
+    }
     return 0;
 }
 

@@ -57,6 +57,13 @@ struct Problem {
     const double* ktap_v;      // [ntaps] values and
     const int* ktap_m;         // [ntaps] offsets m of the taps with |K[m]| >= 1e-18 max|K|
     int ntaps;
+    // Line model (lib/line_models.py:4-61).  The native family is a TIED MULTIPLET: n_comp Gaussians
+    // sharing the centre shift and the width, component k at c + comp_off[k] with relative
+    // amplitude comp_ratio[k] (component 0: offset 0, ratio 1).  n_comp = 1 is
+    // SingleGaussianLineModel (lib/line_models.py:64-109).  The model stays linear in the
+    // amplitude, so the Gibbs step of lib/run.py:456-519 applies unchanged.
+    int n_comp;
+    double comp_off[4], comp_ratio[4];
     const double* kdense;      // [kd_n] the same kernel as a dense window of signed offsets mhi, mhi-1, ... (d3d_pipe.cuh)
     int kd_n, kd_mhi;
     const double* pmin;        // [cube][3]
@@ -136,16 +143,32 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Components 1 .. n_comp-1 of a tied multiplet at distance d = z - c from the first component:
+// sum_k ratio_k exp(-(d - off_k)^2 q), q = 1/(2 w^2).  Out of line and only reached when a
+// multiplet is set (d3d_set_line_model): the single-Gaussian paths keep their exact arithmetic.
+__device__ __noinline__ double extra_components(const Problem& pb, double d, double q) {
+    double s = 0.0;
+    for (int k = 1; k < pb.n_comp; ++k) {
+        const double dk = d - pb.comp_off[k];
+        s = fma(pb.comp_ratio[k], d_exp(-1.0 * (dk * dk) * q), s);
+    }
+    return s;
+}
+
 // lib/line_models.py:98-109 with a = 1
-__device__ __forceinline__ double unit_gaussian(int z, double c, double w) {
+__device__ __forceinline__ double unit_gaussian(const Problem& pb, int z, double c, double w) {
     double d = (double)z - c;
-    return d_exp(d_div(-1.0 * (d * d), 2.0 * (w * w)));
+    double g = d_exp(d_div(-1.0 * (d * d), 2.0 * (w * w)));
+    if (pb.n_comp > 1) g += extra_components(pb, d, d_div(1.0, 2.0 * (w * w)));
+    return g;
 }
 // Same with 1/(2 w^2) hoisted out of the channel loop (one divide per line instead of one per
 // channel; the exponent differs from the reference's by at most one ulp).
-__device__ __forceinline__ double unit_gaussian_r(int z, double c, double inv2w2) {
+__device__ __forceinline__ double unit_gaussian_r(const Problem& pb, int z, double c, double inv2w2) {
     double d = (double)z - c;
-    return d_exp(-1.0 * (d * d) * inv2w2);
+    double g = d_exp(-1.0 * (d * d) * inv2w2);
+    if (pb.n_comp > 1) g += extra_components(pb, d, inv2w2);
+    return g;
 }
 
 // lib/convolution.py:89-120 in direct form: out[j] = sum_i g[i] K[(j-i) mod P]
@@ -244,8 +267,8 @@ __device__ __noinline__ void warp_line_profile(const Problem& pb, const Smem& sm
     // two channels per lane and per pass: independent exp() chains overlap
     for (int z = lane; z < pb.Dp; z += 64) {
         const int z1 = z + 32;
-        const double g0 = z < pb.D ? unit_gaussian_r(z, c, inv2w2) : 0.0;
-        const double g1 = z1 < pb.D ? unit_gaussian_r(z1, c, inv2w2) : 0.0;
+        const double g0 = z < pb.D ? unit_gaussian_r(pb, z, c, inv2w2) : 0.0;
+        const double g1 = z1 < pb.D ? unit_gaussian_r(pb, z1, c, inv2w2) : 0.0;
         g[z] = g0;
         if (z1 < pb.Dp) g[z1] = g1;
     }
@@ -1093,7 +1116,9 @@ __global__ void lines_kernel(const __grid_constant__ Problem pb, const double* p
         const bool on = live && par[ls * 4 + 3] != 0.0;
         if (on && z < D) {
             const double d = (double)z - par[ls * 4 + 1];
-            gw[z] = par[ls * 4 + 0] * exp(-1.0 * (d * d) * par[ls * 4 + 2]);   // lib/line_models.py:109
+            double gv = exp(-1.0 * (d * d) * par[ls * 4 + 2]);                   // lib/line_models.py:109
+            if (pb.n_comp > 1) gv += extra_components(pb, d, par[ls * 4 + 2]);
+            gw[z] = par[ls * 4 + 0] * gv;
         }
         __syncthreads();
         if (live) {
@@ -1162,7 +1187,9 @@ __global__ void __launch_bounds__(256) lines_warp_kernel(const __grid_constant__
             g[k] = 0.0;
             if (on && z < D) {
                 const double d = (double)z - c;
-                g[k] = a * exp(-1.0 * (d * d) * q);                           // lib/line_models.py:109
+                double gv = exp(-1.0 * (d * d) * q);                          // lib/line_models.py:109
+                if (pb.n_comp > 1) gv += extra_components(pb, d, q);
+                g[k] = a * gv;
             }
         }
         if (conv) {
@@ -1296,7 +1323,7 @@ __global__ void clean_kernel(const __grid_constant__ Problem pb, const double* p
     double v = 0.0;
     if (pb.mask[(size_t)cube * HW + site] == 1) {
         const double* p = params + ((size_t)chain * HW + site) * 3;
-        v = p[0] * unit_gaussian(z, p[1], p[2]);
+        v = p[0] * unit_gaussian(pb, z, p[1], p[2]);
     }
     out[i] = v;
 }

@@ -931,8 +931,12 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_AP(PIPE_ROLE_PARAMS) {
                 if (z0 < D) {
                     const double d0 = (double)z0 - c_prof, d1 = (double)(z0 + 1) - c_prof;
                     // (one out-of-line copy of exp: code footprint, see the note on the I-cache)
-                    const double g0 = d_exp(-1.0 * (d0 * d0) * inv2w2);
-                    const double g1 = z0 + 1 < D ? d_exp(-1.0 * (d1 * d1) * inv2w2) : 0.0;
+                    double g0 = d_exp(-1.0 * (d0 * d0) * inv2w2);
+                    double g1 = z0 + 1 < D ? d_exp(-1.0 * (d1 * d1) * inv2w2) : 0.0;
+                    if (pb.n_comp > 1) {                         // tied multiplet (d3d_set_line_model)
+                        g0 += extra_components(pb, d0, inv2w2);
+                        if (z0 + 1 < D) g1 += extra_components(pb, d1, inv2w2);
+                    }
                     if (pb.has_lsf) {
                         const int GN = pv.GN;
 #pragma unroll

@@ -591,7 +591,9 @@ sweep_seq_slide_kernel(const __grid_constant__ Problem pb, long long it0_all, lo
 #pragma unroll 1
                     for (int z = lane; z < D; z += 32) {
                         const double d0 = (double)z - c_prof;
-                        g_buf[z] = exp(-1.0 * (d0 * d0) * inv2w2);
+                        double gv = exp(-1.0 * (d0 * d0) * inv2w2);
+                        if (pb.n_comp > 1) gv += extra_components(pb, d0, inv2w2);
+                        g_buf[z] = gv;
                     }
                     __syncwarp();
                     if (pb.has_lsf) {

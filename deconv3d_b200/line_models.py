@@ -12,7 +12,7 @@ evaluation of a single line.
 """
 import numpy as np
 
-__all__ = ['LineModel', 'SingleGaussianLineModel']
+__all__ = ['LineModel', 'SingleGaussianLineModel', 'TiedGaussiansLineModel']
 
 
 class LineModel(object):
@@ -75,3 +75,38 @@ class SingleGaussianLineModel(LineModel):
         """a * exp(-(x-c)^2 / (2 w^2))   (lib/line_models.py:98-109)."""
         x = np.asarray(x)
         return a * np.exp(-1. * (x - c) ** 2 / (2. * w ** 2))
+
+
+class TiedGaussiansLineModel(SingleGaussianLineModel):
+    """A multiplet of Gaussian lines tied to one another: component k sits ``offsets[k]`` channels
+    from the first one and carries ``ratios[k]`` times its amplitude; all share the centre shift
+    and the width.  Parameters stay (a, c, w) -- amplitude and centre of the FIRST component -- and
+    the model stays linear in ``a``, which remains the Gibbs parameter (lib/run.py:456-519).
+    Examples: [NII]6548 - Halpha - [NII]6583, the [OII]3726,3729 doublet.
+
+    This is the family of user models (lib/line_models.py:4-61) the CUDA sweep evaluates natively
+    (``d3d_set_line_model``); at most 4 components."""
+
+    native = True
+
+    def __init__(self, offsets, ratios):
+        offsets = np.asarray(offsets, dtype=np.float64).ravel()
+        ratios = np.asarray(ratios, dtype=np.float64).ravel()
+        if offsets.shape != ratios.shape or not 1 <= offsets.size <= 4:
+            raise ValueError("offsets and ratios must hold the same number (1..4) of components.")
+        if ratios[0] == 0:
+            raise ValueError("The first component carries the amplitude: its ratio must not be 0.")
+        self.offsets = offsets - offsets[0]
+        self.ratios = ratios / ratios[0]
+
+    def native_components(self):
+        """(offsets, ratios) handed to the device."""
+        return self.offsets, self.ratios
+
+    def modelize(self, runner, x, parameters):
+        x = np.asarray(x)
+        a, c, w = parameters[0], parameters[1], parameters[2]
+        unit = np.exp(-1. * (x - c) ** 2 / (2. * w ** 2))
+        for off, ratio in zip(self.offsets[1:], self.ratios[1:]):
+            unit = unit + ratio * np.exp(-1. * (x - c - off) ** 2 / (2. * w ** 2))
+        return a * unit

@@ -179,6 +179,8 @@ class Run(object):
             data, variance_scalar if variance_scalar is not None else self.variance_cube,
             self.fsf, self.lsf, min_boundaries, max_boundaries, jumping_amplitude,
             self.gibbs_apriori_variance, mask=self.mask, chains_per_cube=n_chains)
+        if self._native_components is not None:
+            ctx.set_line_model(*self._native_components)
 
         # -- initial parameters (lib/run.py:293-314) ------------------------------------
         if initial_parameters is not None:
@@ -308,19 +310,27 @@ class Run(object):
         return cube, scalar
 
     def _require_native_model(self):
-        """The kernels evaluate SingleGaussianLineModel + Cauchy jump + row-major masked
-        iteration.  Anything else would need a CPU path, which this package does not
-        have -- fail loudly instead (SURVEY.md section 7 'Hard parts')."""
+        """The kernels evaluate the tied-multiplet family of line models (one Gaussian =
+        SingleGaussianLineModel, several = TiedGaussiansLineModel; ``d3d_set_line_model``) with
+        the Cauchy jump and the row-major masked iteration.  Anything else would need a CPU path,
+        which this package does not have -- fail loudly instead (SURVEY.md section 7 'Hard
+        parts')."""
+        from .line_models import TiedGaussiansLineModel
         m = type(self.model)
-        native = (m.modelize is SingleGaussianLineModel.modelize
-                  and getattr(m, 'gaussian') is SingleGaussianLineModel.gaussian
+        single = (m.modelize is SingleGaussianLineModel.modelize
+                  and getattr(m, 'gaussian') is SingleGaussianLineModel.gaussian)
+        tied = isinstance(self.model, TiedGaussiansLineModel) and \
+            m.modelize is TiedGaussiansLineModel.modelize and \
+            m.native_components is TiedGaussiansLineModel.native_components
+        native = ((single or tied)
                   and m.post_jump is LineModel.post_jump
                   and self.model.gibbs_parameter_index() == 0
                   and list(self.model.parameters()) == ['a', 'c', 'w'])
         if not native:
             raise NotImplementedError(
-                "deconv3d_b200 evaluates SingleGaussianLineModel on the GPU; custom "
-                "modelize/post_jump/Gibbs parameters are not supported (no CPU fallback).")
+                "deconv3d_b200 evaluates SingleGaussianLineModel and TiedGaussiansLineModel on the "
+                "GPU; custom modelize/post_jump/Gibbs parameters are not supported (no CPU fallback).")
+        self._native_components = self.model.native_components() if tied else None
         if type(self).jump_from is not Run.jump_from or \
                 type(self).spaxel_iterator is not Run.spaxel_iterator:
             raise NotImplementedError(

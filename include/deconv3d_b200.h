@@ -246,6 +246,16 @@ int d3d_chain_mean(d3d_ctx* ctx, const double* chain, int64_t n_rows, int64_t fi
 int d3d_get_counters(d3d_ctx* ctx, int64_t* kernel_launches,
                      int64_t* last_sweep_bytes, int64_t* last_sweep_site_updates);
 
+/* Line model (replaces the plug-in hook lib/line_models.py:4-61 -- LineModel.modelize called at
+ * lib/run.py:673, 604, 1016 -- for the family the device evaluates): a TIED MULTIPLET of
+ * n_components (1..4) Gaussians that share the centre shift and the width,
+ *     line(z) = a * sum_k ratios[k]/ratios[0] * exp(-(z - c - (offsets[k]-offsets[0]))^2 / (2 w^2)),
+ * parameters (a, c, w) as in SingleGaussianLineModel (lib/line_models.py:64-109; n_components = 1,
+ * the state after d3d_set_problem).  a is the amplitude of component 0 and stays the Gibbs
+ * parameter (lib/run.py:456-519: the model is linear in it).  Examples: [NII]-Halpha-[NII], the
+ * [OII] doublet.  Call after d3d_set_problem, before d3d_forward / d3d_sweep. */
+int d3d_set_line_model(d3d_ctx* ctx, int n_components, const double* offsets, const double* ratios);
+
 /* Bench support: measured FP64 FMA peak of the context's device in TFLOP/s (8 independent
  * DFMA chains per thread, every SM full, best of 5) -- the denominator of the FP64-pipe
  * fractions bench.py reports for the forward-model stencil and the sweep kernel.  Nothing in

@@ -282,3 +282,102 @@ def test_balanced_schedule_with_stopped_chains(nat, monkeypatch, pipe):
         assert np.array_equal(ch[0, 1:nrow], chain[k, 1:nrow]), k
         assert np.array_equal(c1.get_residual()[0], res[k]), k
         c1.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# f-4: line models beyond the single Gaussian (lib/line_models.py:4-61): tied multiplets
+# ---------------------------------------------------------------------------------------------
+MULTIPLETS = [([0.0, 3.2], [1.0, 0.6]),                       # a doublet ([OII]-like)
+              ([0.0, -4.5, 6.1], [1.0, 0.11, 0.33])]          # [NII] - Halpha - [NII]-like triplet
+
+
+@pytest.mark.parametrize('comp', MULTIPLETS)
+def test_multiplet_forward_model_vs_oracle(nat, comp):
+    """Forward model (lib/run.py:999-1031) of a tied multiplet, 1e-12 relative (fp64)."""
+    from oracle import reference_port as port
+    from conftest import load_golden
+    g = load_golden('ref_run_A')
+    data, fsf, lsf = g['data'], g['fsf'], g['lsf']
+    D, H, W = data.shape
+    rs = np.random.RandomState(4)
+    params = np.dstack([rs.rand(H, W) * 5, 2 + rs.rand(H, W) * (D - 4), 0.6 + rs.rand(H, W) * 2])
+    pmin, pmax = port.single_gaussian_boundaries(data, fsf)
+    ctx = nat.Context(0, nat.F64)
+    ctx.set_problem(data, np.array([0.01]), fsf, lsf, pmin, pmax, [0, .1, .1], float(pmax[0]) ** 2)
+    ctx.set_line_model(*comp)
+    ctx.set_params(params[None])
+    sim, _ = ctx.forward(want_sim=True, write_err=True)
+    with port.line_model(*comp):
+        err_ref = port.compute_error_in_one_step(data, params, fsf, lsf, np.ones((H, W)))
+        clean_ref = port.simulate_clean(data.shape, params, np.ones((H, W)))
+    scale = np.abs(data - err_ref).max()
+    np.testing.assert_allclose(sim[0], data - err_ref, rtol=1e-12, atol=1e-12 * scale)
+    np.testing.assert_allclose(ctx.get_residual()[0], err_ref, rtol=0, atol=1e-12 * np.abs(data).max())
+    np.testing.assert_allclose(ctx.simulate_clean(params[None])[0], clean_ref, rtol=1e-12, atol=1e-14)
+    # one Gaussian again: the model is a property of the context, not of the build
+    ctx.set_line_model(None)
+    sim1, _ = ctx.forward(want_sim=True, write_err=False)
+    err1 = port.compute_error_in_one_step(data, params, fsf, lsf, np.ones((H, W)))
+    np.testing.assert_allclose(sim1[0], data - err1, rtol=1e-12, atol=1e-12 * scale)
+    ctx.close()
+
+
+@pytest.mark.parametrize('mode,pipe', [('seq', '0'), ('seq', '2'), ('colour', '1')])
+@pytest.mark.parametrize('comp', MULTIPLETS[:1] + MULTIPLETS[1:])
+def test_multiplet_chain_vs_oracle(nat, monkeypatch, mode, pipe, comp):
+    """Sweeps with a tied multiplet against the oracle running the same model: identical
+    decisions, chains to 1e-9 -- sliding-window kernel, pipelined kernel and coloured mode."""
+    from oracle import reference_port as port
+    from conftest import load_golden
+    monkeypatch.setenv('D3D_PIPE', pipe)
+    g = load_golden('ref_run_C')                         # mask + variance cube + D = 16 (full wrap)
+    data, fsf, lsf = g['data'], g['fsf'], g['lsf']
+    var, mask_in, init = g['in_variance'], g['in_mask'], g['in_initial_parameters']
+    D, H, W = data.shape
+    max_it = 8
+    order = None
+    m_for_order = port.prepare_mask(data, mask_in.copy())
+    if mode == 'colour':
+        order = port.colour_class_order(m_for_order, fsf.shape[0], fsf.shape[1])
+    with port.line_model(*comp):
+        from oracle import streams
+        trace = {}
+        ref = port.run_chain(data, fsf, lsf, streams.PhiloxStream(3, 0), mask=mask_in.copy(),
+                             variance_cube=var, initial_parameters=init, jump_amplitude=0.3,
+                             gibbs_apriori_variance=50.0, max_iterations=max_it, trace=trace,
+                             rtnorm_tables=_tables(), site_order=order, min_acceptance_rate=0.0,
+                             refresh_every=0)
+    pmin, pmax = port.single_gaussian_boundaries(data, fsf)
+    ctx = nat.Context(0, nat.F64)
+    ctx.set_rtnorm_tables(*_tables())
+    ctx.set_rng(3, 0)
+    ctx.set_problem(data, var, fsf, lsf, pmin, pmax, [0, .3, .3], 50.0, mask=ref['mask'])
+    ctx.set_line_model(*comp)
+    ctx.set_params(np.asarray(init, float)[None])
+    chain = np.zeros((1, max_it, H, W, 3))
+    lik = np.zeros((1, max_it, H, W))
+    chain[0, 0] = ctx.get_params()[0]
+    ctx.forward(write_err=True)
+    acc, its, _ = ctx.sweep(1, max_it - 1, mode=nat.SEQ_EXACT if mode == 'seq' else nat.COLOURED,
+                            refresh_every=0, min_acceptance_rate=0.0, chain_out=chain, lik_out=lik)
+    _check_chain(ref, trace, chain[0], lik[0], int(acc[0]), int(its[0]), ctx.get_residual()[0], data)
+    ctx.close()
+
+
+def test_run_dropin_with_tied_multiplet(nat):
+    """``Run(model=TiedGaussiansLineModel(...))`` through the reference's plug-in argument
+    (lib/run.py:95-109 `model=`): convolved output cube = forward model of the parameters."""
+    from deconv3d_b200 import Run, MUSE, TiedGaussiansLineModel
+    from oracle import reference_port as port
+    from conftest import load_golden
+    g = load_golden('ref_run_A')
+    data = g['data']
+    inst = MUSE(fsf_fwhm=0.5)
+    model = TiedGaussiansLineModel([0.0, 3.2], [1.0, 0.6])
+    run = Run(inst.build_cube(data), inst, model=model, max_iterations=6, seed=5)
+    with port.line_model([0.0, 3.2], [1.0, 0.6]):
+        ref = data - port.compute_error_in_one_step(data, run.parameters, run.fsf, run.lsf, run.mask)
+    np.testing.assert_allclose(run.convolved_cube.data, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    line = run.model.modelize(run, range(0, data.shape[0]), run.parameters[3, 4])
+    with port.line_model([0.0, 3.2], [1.0, 0.6]):
+        np.testing.assert_allclose(line, port.modelize(data.shape[0], run.parameters[3, 4]), rtol=1e-14)

@@ -141,3 +141,25 @@ def test_fits_round_trip(tmp_path):
     assert abs(cube.get_step(0).to('um').value - 1.25e-4) < 1e-18
     with pytest.raises(IOError):
         cube.to_fits(path)
+
+
+def test_tied_gaussians_line_model_vs_oracle():
+    """TiedGaussiansLineModel (the natively evaluated family of user line models,
+    lib/line_models.py:4-61) against the oracle's multiplet, and the interface it keeps."""
+    from deconv3d_b200 import TiedGaussiansLineModel, SingleGaussianLineModel, LineModel
+    from oracle import reference_port as port
+    m = TiedGaussiansLineModel([10.0, 13.2, 5.0], [2.0, 1.2, 0.5])
+    assert isinstance(m, LineModel) and m.parameters() == ['a', 'c', 'w'] and m.gibbs_parameter_index() == 0
+    off, rat = m.native_components()
+    assert np.allclose(off, [0, 3.2, -5.0]) and np.allclose(rat, [1, 0.6, 0.25])
+    p = [3.5, 14.2, 1.7]
+    with port.line_model([10.0, 13.2, 5.0], [2.0, 1.2, 0.5]):
+        assert np.allclose(m.modelize(None, range(0, 30), p), port.modelize(30, p), rtol=1e-15, atol=0)
+    # one component = the single Gaussian, bit for bit
+    one = TiedGaussiansLineModel([0.0], [1.0])
+    assert np.array_equal(one.modelize(None, range(0, 30), p), SingleGaussianLineModel().modelize(None, range(0, 30), p))
+    import pytest
+    with pytest.raises(ValueError):
+        TiedGaussiansLineModel([0, 1], [0.0, 1.0])
+    with pytest.raises(ValueError):
+        TiedGaussiansLineModel([0, 1, 2, 3, 4], [1, 1, 1, 1, 1])
