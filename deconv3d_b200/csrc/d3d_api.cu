@@ -155,6 +155,7 @@ struct d3d_ctx {
     void* rt_x = nullptr; void* rt_yu = nullptr; void* rt_nc = nullptr;
     double* d_lines = nullptr;          // [n_chains][H][W][Dp] scratch of the forward model
     int tap_runs = 0, tap_run2 = 0;     // runs of consecutive LSF tap offsets; first tap of the second run
+    int tap_reach = 0;                  // largest |signed offset| of a significant LSF tap
     int threads = 256, ne = 0;          // sweep launch configuration (row-mapped kernels)
     int generic_threads = 256;
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
@@ -545,6 +546,7 @@ extern "C" int d3d_set_problem(d3d_ctx* c, int n_cubes, int chains_per_cube, int
         if (!any) { mlo = mhi = 0; }
         for (int t = 0; t <= mhi - mlo; ++t) kdense.push_back(hk[((mhi - t) % pb.P + pb.P) % pb.P]);
         pb.kd_n = (int)kdense.size(); pb.kd_mhi = mhi;
+        c->tap_reach = std::max(std::abs(mlo), std::abs(mhi));
     }
     // runs of consecutive tap offsets (lines_warp_kernel rotates its buffer inside a run)
     c->tap_runs = tapm.empty() ? 0 : 1;
@@ -740,7 +742,23 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
         // per lane; the shared-memory kernel for deeper cubes (and under D3D_LINES_SMEM, for A/B runs)
         const int R = pb.P <= 32 ? 1 : pb.P <= 64 ? 2 : pb.P <= 128 ? 4 : 0;
         const size_t wblocks = (size_t)pb.n_chains * ((HW + LINES_SPB - 1) / LINES_SPB);
-        if (R && pb.Dp <= 32 * R && pb.ntaps <= 32 * R && c->tap_runs <= 2 && wblocks < ((size_t)1 << 31) &&
+        // one thread per spaxel, spectrum in registers (lines_lane_kernel): needs the depth and
+        // the reach of the significant LSF taps among the instantiated pairs
+        bool lane_done = false;
+        if (!getenv("D3D_LINES_WARP") && !getenv("D3D_LINES_SMEM")) {
+            const int mh = c->tap_reach;                 // max |signed offset| of a significant tap
+            const unsigned lb = (unsigned)((total + 127) / 128);
+#define D3D_LANE(DPV, MHV)                                                                          \
+            if (!lane_done && pb.Dp == DPV && mh <= MHV) {                                          \
+                lines_lane_kernel<DPV, MHV><<<lb, 128, 0, c->stream>>>(pb, d_params, c->d_lines, convolve); \
+                lane_done = true;                                                                   \
+            }
+            D3D_LANE(16, 7) D3D_LANE(30, 8) D3D_LANE(30, 15) D3D_LANE(32, 8) D3D_LANE(32, 15)
+            D3D_LANE(40, 8) D3D_LANE(40, 15) D3D_LANE(64, 8) D3D_LANE(64, 15)
+#undef D3D_LANE
+        }
+        if (lane_done) {
+        } else if (R && pb.Dp <= 32 * R && pb.ntaps <= 32 * R && c->tap_runs <= 2 && wblocks < ((size_t)1 << 31) &&
             !getenv("D3D_LINES_SMEM")) {
             const unsigned wb = (unsigned)wblocks;
             if (R == 1) lines_warp_kernel<1><<<wb, 256, 0, c->stream>>>(pb, d_params, c->d_lines, convolve, c->tap_run2);

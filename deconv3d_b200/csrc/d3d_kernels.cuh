@@ -1329,6 +1329,105 @@ __global__ void clean_kernel(const __grid_constant__ Problem pb, const double* p
 }
 
 // ---------------------------------------------------------------------------
+// Spectral pass, ONE THREAD PER SPAXEL (lib/run.py:1012-1024: line model, then convolve_1d with
+// the LSF).  The whole spectrum of a spaxel lives in the registers of its thread: DP_T Gaussian
+// values, then out[z] = sum_{|m| <= MH} K[m mod P] * g[(z - m) mod P] -- the circular
+// convolution of lib/convolution.py:89-160 in direct form -- fully unrolled with compile-time
+// indices (P = smallest power of two >= DP_T, exactly the reference's padded length), so the
+// inner work is DFMA only: no shared-memory traffic, no shuffles, no per-tap index arithmetic.
+// The warp-per-spaxel kernel above spends ~380 warp instructions per spaxel (taps through
+// shuffles, one exp per lane); this one ~70, of which 32 exp() calls.  Output rows are written
+// with 16-byte stores (a thread owns DP_T contiguous doubles).
+// Taken when every significant tap lies within MH channels and 2 MH + 1 <= P.
+// ---------------------------------------------------------------------------
+template <int N> struct NextPow2 { static const int value = N <= 1 ? 1 : 2 * NextPow2<(N + 1) / 2>::value; };
+template <> struct NextPow2<1> { static const int value = 1; };
+template <> struct NextPow2<0> { static const int value = 1; };
+
+// exp(x) for x <= 0, table driven: x = (64 n' + j) ln2/64 + r, |r| <= ln2/128, so that
+// exp(x) = 2^n' * 2^(j/64) * exp(r) with a degree-5 polynomial for exp(r) (|r|^6/720 < 4e-17).
+// About 14 instructions instead of ~45 for the library routine; relative error <= ~2 ulp.
+// Results below 2^-995 are flushed to zero (the tail of a line profile, far below the 1e-12
+// relative bar of the convolved cubes).  tab64[j] = 2^(j/64) sits in shared memory.
+__device__ __forceinline__ double exp_neg_tab(double x, const double* tab64) {
+    const double MAGIC = 6755399441055744.0;                  // 1.5 * 2^52: round to nearest integer
+    const double t = fma(x, 92.33248261689366, MAGIC);        // 64 / ln 2
+    const int ni = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -1.0830424696223417e-02, x);           // ln2/64, high part
+    r = fma(nd, -2.5728046223276688e-14, r);                  // ln2/64, low part
+    double p = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    p = fma(p, r, 1.6666666666666666e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = tab64[ni & 63] * p;
+    const int e = ni >> 6;                                    // floor(ni / 64) <= 0
+    const double scaled = __hiloint2double(__double2hiint(v) + (e << 20), __double2loint(v));
+    // x <= -690: below 2^-995, flushed to zero (also keeps ni inside 32 bits for any finite x);
+    // NaN (a line of width 0 sitting on a channel: 0 * inf, as in the reference) stays NaN
+    return x > -690.0 ? scaled : (x <= -690.0 ? 0.0 : x);
+}
+
+template <int DP_T, int MH>
+__global__ void __launch_bounds__(128)
+lines_lane_kernel(const __grid_constant__ Problem pb, const double* __restrict__ params,
+                  double* __restrict__ lines, int convolve) {
+    constexpr int P = NextPow2<DP_T>::value;
+    constexpr int NT = 2 * MH + 1;
+    static_assert(NT <= P, "the tap window must not wrap onto itself");
+    __shared__ double sK[NT];
+    __shared__ double tab64[64];
+    for (int t = threadIdx.x; t < NT; t += blockDim.x) sK[t] = pb.kcirc[((t - MH) % P + P) % P];
+    for (int t = threadIdx.x; t < 64; t += blockDim.x) tab64[t] = exp2((double)t * (1.0 / 64.0));
+    __syncthreads();
+    const size_t HW = (size_t)pb.H * pb.W;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)pb.n_chains * HW) return;
+    const size_t chain = i / HW, site = i - chain * HW;
+    const bool on = pb.mask[(size_t)(chain / pb.chains_per_cube) * HW + site] == 1;
+    const double* p = params + i * 3;
+    const double a = p[0], c = p[1], w = p[2];
+    const double q = 1.0 / (2.0 * (w * w));
+    const int D = pb.D;
+    double g[DP_T];
+#pragma unroll
+    for (int ch = 0; ch < DP_T; ++ch) {
+        const double d = (double)ch - c;
+        double gv = exp_neg_tab(-1.0 * (d * d) * q, tab64);                 // lib/line_models.py:109
+        if (pb.n_comp > 1) gv += extra_components(pb, d, q);
+        g[ch] = (on && ch < D) ? a * gv : 0.0;
+    }
+    double* out = lines + i * DP_T;
+    if (!(convolve && pb.has_lsf)) {                                        // lib/run.py:675-676
+#pragma unroll
+        for (int z = 0; z < DP_T; z += 2) *(double2*)(out + z) = make_double2(g[z], g[z + 1]);
+        return;
+    }
+    double k[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) k[t] = sK[t];
+#pragma unroll
+    for (int z = 0; z < DP_T; z += 2) {
+        double o[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                // tap m = t - MH reads channel (z - m) mod P; channels >= DP_T are zero padding
+                const int ch = (((z + u) - (t - MH)) % P + P) % P;
+                if (ch < DP_T) {
+                    if (t & 1) a1 = fma(k[t], g[ch], a1); else a0 = fma(k[t], g[ch], a0);
+                }
+            }
+            o[u] = (z + u < D) ? a0 + a1 : 0.0;
+        }
+        *(double2*)(out + z) = make_double2(o[0], o[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Layout conversion between the reference layout [n][D][H][W] float64 and the
 // device layout [n][H][W][Dp] T.
 //   mode 0: plain copy (data; NaN -> 0)          mode 1: reciprocal (variance -> 1/var;

@@ -179,29 +179,39 @@ def test_forward_random_params_vs_oracle(nat, shape, fsf_kind, lsf_fwhm):
                                rtol=1e-12, atol=1e-300)
 
 
-@pytest.mark.parametrize('D', [12, 32, 40, 64, 100])
-def test_spectral_pass_warp_shuffle_equals_shared_memory_kernel(nat, monkeypatch, D):
-    """The warp-shuffle spectral pass (lines_warp_kernel, registers + __shfl) and the
-    shared-memory one (lines_kernel) keep the same summation order: bit-identical cubes."""
+@pytest.mark.parametrize('D', [12, 16, 30, 32, 40, 64, 100])
+def test_spectral_pass_variants_agree(nat, monkeypatch, D):
+    """Three spectral passes: one thread per spaxel with the spectrum in registers
+    (lines_lane_kernel, the default where it is instantiated), one warp per spaxel
+    (lines_warp_kernel, registers + __shfl) and the shared-memory one (lines_kernel).  The last
+    two keep the same summation order: bit-identical cubes; the first one sums the taps in
+    window order and uses a table-driven exp: equal to 1e-13 of the cube's scale."""
     port, _, _ = _oracle()
     H, W = 7, 9
     rs = np.random.RandomState(D)
     fsf = port.moffat_fsf_image((5, 5), 0.2, fwhm_arcsec=0.8, beta=2.5)
-    lsf = port.gaussian_lsf_vector(0.0005, 1.25e-4, D)
+    lsf = port.gaussian_lsf_vector(0.0005 if D > 16 else 0.00025, 1.25e-4, D)
     data = synthetic(D, H, W, 5)
     mask = (rs.rand(H, W) > 0.2).astype(float)
     params = np.dstack([rs.rand(H, W) * 9, rs.rand(H, W) * (D - 1), 0.3 + rs.rand(H, W) * 4])
+    params[0, 0] = [3.0, D / 2., 0.02]                # a line far narrower than a channel
+    params[0, 1] = [3.0, D - 1.0, 40.0]               # and one far wider than the cube
     out = []
-    for smem in (False, True):
-        if smem:
-            monkeypatch.setenv('D3D_LINES_SMEM', '1')
+    for env in (None, 'D3D_LINES_WARP', 'D3D_LINES_SMEM'):
+        if env:
+            monkeypatch.setenv(env, '1')
         ctx, _, _ = make_ctx(nat, data, np.array([0.01]), fsf, lsf, mask=mask)
         ctx.set_params(params[None])
         sim, _ = ctx.forward(want_sim=True, write_err=True)
         out.append((sim.copy(), ctx.get_residual().copy()))
         ctx.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[1][0], out[2][0])
+    assert np.array_equal(out[1][1], out[2][1])
+    scale = np.abs(out[2][0]).max()
+    np.testing.assert_allclose(out[0][0], out[2][0], rtol=0, atol=1e-13 * scale)
+    np.testing.assert_allclose(out[0][1], out[2][1], rtol=0, atol=1e-13 * scale)
+    err_ref = port.compute_error_in_one_step(data, params, fsf, lsf, mask)
+    np.testing.assert_allclose(out[0][1][0], err_ref, rtol=0, atol=1e-12 * max(scale, np.abs(data).max()))
 
 
 @pytest.mark.parametrize('var_kind', ['scalar', 'cube'])
