@@ -60,17 +60,26 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(data + ((size_t)gy * W + gx) * Dp + pz));
             }
     }
+    // Halo tile: global -> shared memory with cp.async (LDGSTS, 16 bytes per copy, no register
+    // staging): every copy of the thread is in flight at once, so the staging phase costs about one
+    // memory round trip instead of one per group of four loads (2 CTAs of 8 warps per SM cannot
+    // hide them otherwise).  Positions outside the field are the zero 'same' border.
 #pragma unroll 4
     for (int i = tid; i < hy * hx * (ZC / 2); i += 256) {    // double2 granularity
         const int zq = i & 7, s = i >> 3;
         const int sy = s / hx, sx = s - sy * hx;
         const int gy = ty0 + sy - pb.fhh, gx = tx0 + sx - pb.fhw;
         const int z = z0 + 2 * zq;
-        double2 v = make_double2(0.0, 0.0);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W && z < Dp)
-            v = *(const double2*)(lc + ((size_t)gy * W + gx) * Dp + z);
-        *(double2*)(tile + (size_t)s * ZC + 2 * zq) = v;
+        double* dst = tile + (size_t)s * ZC + 2 * zq;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W && z < Dp) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(lc + ((size_t)gy * W + gx) * Dp + z) : "memory");
+        } else {
+            *(double2*)dst = make_double2(0.0, 0.0);
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int zq = tid & 7, xb = (tid >> 3) & 3, oy = tid >> 5;
@@ -189,11 +198,16 @@ stencil_wide_kernel(const __grid_constant__ Problem pb, const double* __restrict
         const int sy = s / hx, sx = s - sy * hx;
         const int gy = ty0 + sy - pb.fhh, gx = tx0 + sx - pb.fhw;
         const int z = z0 + 2 * zq;
-        double2 v = make_double2(0.0, 0.0);
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W && z < Dp)
-            v = *(const double2*)(lc + ((size_t)gy * W + gx) * Dp + z);
-        *(double2*)(tile + ((size_t)sy * hxp + sx) * ZC + 2 * zq) = v;
+        double* dst = tile + ((size_t)sy * hxp + sx) * ZC + 2 * zq;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W && z < Dp) {      // cp.async staging, as in the tiled kernel
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(lc + ((size_t)gy * W + gx) * Dp + z) : "memory");
+        } else {
+            *(double2*)dst = make_double2(0.0, 0.0);
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     const int zq = tid & 1, oy = ((tid >> 6) << 2) | ((tid >> 1) & 3), xb = (tid >> 3) & 7;
