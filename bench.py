@@ -157,29 +157,33 @@ class ClockSampler(object):
                 'power_w_max': max(float(s[2]) for s in self.samples)}
 
 
-def measured_traffic(workload, chains, sweeps, dtype, mode):
+def measured_traffic(workload, chains, sweeps, dtype, mode, kernel):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/*_traffic.json), only when it was taken on the same workload."""
+    (profiles/*_traffic.json), only when it was taken on the same workload AND the same kernel
+    (the library picks the sweep kernel by problem shape and chain count; d3d_last_kernel)."""
     import glob
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_traffic.json')), reverse=True):
         try:
             t = json.load(open(path))
             m = t.get('match', {})
             if (m.get('workload') == workload and m.get('chains') == chains and
-                    m.get('sweeps') == sweeps and m.get('dtype') == dtype and m.get('mode') == mode):
+                    m.get('sweeps') == sweeps and m.get('dtype') == dtype and m.get('mode') == mode and
+                    str(t.get('kernel', '')).split('<')[0] == str(kernel).split('<')[0]):
                 return float(t['dram_bytes_per_launch']), os.path.relpath(path, ROOT)
         except Exception:               # noqa: BLE001
             continue
     return None, None
 
 
-def measured_profile():
+def measured_profile(kernel):
     """Issue-slot utilisation of the dominant kernel from the committed ncu --set full capture
-    (profiles/*_sweep_metrics.json, written by profiles/tools/ncu_lines.py --metrics)."""
+    (profiles/*_sweep_metrics.json) of that same kernel."""
     import glob
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_sweep_metrics.json')), reverse=True):
         try:
             t = json.load(open(path))
+            if str(t.get('kernel', '')).split('<')[0] != str(kernel).split('<')[0]:
+                continue
             return {'issue_slot_frac': float(t['issue_slot_frac']), 'source': os.path.relpath(path, ROOT)}
         except Exception:               # noqa: BLE001
             continue
@@ -428,8 +432,9 @@ def main():
         return
 
     peak, peak_src = measured_peak()
-    traffic, traffic_src = measured_traffic(args.workload, n_chains, sweeps, args.dtype, args.mode)
-    prof = measured_profile()
+    traffic, traffic_src = measured_traffic(args.workload, n_chains, sweeps, args.dtype, args.mode,
+                                            kernel_name(ctx, args.mode))
+    prof = measured_profile(kernel_name(ctx, args.mode))
     kern_total_ms = float(np.sum(kern_ms))
     achieved = bytes_algo / (kern_total_ms * 1e-3) / 1e9
     state_mb = n_chains * D * H * W * (8 if args.dtype == 'f64' else 4) / 1e6

@@ -24,20 +24,43 @@ using namespace d3d;
 
 // pipelined sweep kernel (d3d_pipe.cuh): look-ahead, producer warps and thread bound of the
 // instantiation that ships; -D overrides are for the A/B builds of profiles/tools
-#ifndef D3D_PIPE_L
-#define D3D_PIPE_L 2
+// Two instantiations of the pipelined sweep (d3d_pipe.cuh; measured in profiles/r02_notes.md):
+//   "few"  (chains <= 2/5 of the SMs): per-site producer warps (2 + 2), look-ahead 2, 16 warps at cfg2.
+//          Fastest per chain (0.62 M evals/s for one chain) while the chip is partly filled.
+//   "many": ONE batched producer warp (8 sites per pass), look-ahead 1, 13 warps at cfg2.  The
+//          smallest per-site instruction footprint: 59.8 M evals/s with every SM busy.
+#ifndef D3D_PIPE_LMAX
+#define D3D_PIPE_LMAX 2         // the cross-term tables are built for this look-ahead
 #endif
-#ifndef D3D_PIPE_NA
-#define D3D_PIPE_NA 3
+#ifndef D3D_PIPEF_L
+#define D3D_PIPEF_L 2
 #endif
-#ifndef D3D_PIPE_NP
-#define D3D_PIPE_NP 3
+#ifndef D3D_PIPEF_NA
+#define D3D_PIPEF_NA 2
+#endif
+#ifndef D3D_PIPEF_NP
+#define D3D_PIPEF_NP 2
+#endif
+#ifndef D3D_PIPEF_MAXT
+#define D3D_PIPEF_MAXT 512      // 16 warps at cfg2: 128 registers per thread
+#endif
+#ifndef D3D_PIPEM_L
+#define D3D_PIPEM_L 1
+#endif
+#ifndef D3D_PIPEM_NPW
+#define D3D_PIPEM_NPW 1
+#endif
+#ifndef D3D_PIPEM_MAXT
+#define D3D_PIPEM_MAXT 416      // 13 warps at cfg2: 152 registers per thread
 #endif
 #ifndef D3D_PIPE_NX
-#define D3D_PIPE_NX 2
+#define D3D_PIPE_NX 1
 #endif
-#ifndef D3D_PIPE_MAXT
-#define D3D_PIPE_MAXT 640
+// chains up to which the per-site producers win: 2/5 of the SMs (A/B on 148 SMs, cycles per site:
+// 37 chains 3 751 vs 4 712, 74 chains 5 043 vs 4 722 -- the curves cross near 60)
+#ifndef D3D_PIPE_FEW_NUM
+#define D3D_PIPE_FEW_NUM 2
+#define D3D_PIPE_FEW_DEN 5
 #endif
 
 static thread_local std::string g_last_error;
@@ -161,7 +184,8 @@ struct d3d_ctx {
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
     static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
     // pipelined sweep kernel (d3d_pipe.cuh): look-ahead L, producer warps, launch shape
-    bool use_pipe = false; int pipe_L = 2, pipe_NA = 3, pipe_NP = 3, pipe_threads = 0; size_t pipe_smem = 0;
+    // pipelined sweep: [0] = per-site producers (few chains), [1] = batched producer (many chains)
+    bool use_pipe[2] = {false, false}; int pipe_threads[2] = {0, 0}; size_t pipe_smem[2] = {0, 0};
     int* d_sites_row = nullptr; int* d_run_start = nullptr; double mean_run = 0.0;
     void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
     long long sched_C = -1, sched_S = -1; int sched_G = -1, sched_max_items = 1; size_t sched_flat = 0;
@@ -317,18 +341,20 @@ static void choose_launch(d3d_ctx* c) {
                        (long long)pb.H * pb.W * pb.W < 0xffffffffLL;   // multiply-high site decode
         if (const char* e = getenv("D3D_SLIDE")) c->use_slide = c->use_slide && atoi(e) != 0;
         // pipelined variant: fw + L + 1 column groups + producer / cross-term / decision warps
-        {
-            c->pipe_L = D3D_PIPE_L; c->pipe_NA = D3D_PIPE_NA; c->pipe_NP = D3D_PIPE_NP;
-            const int ng = pb.fw + c->pipe_L + 1;
+        for (int m = 0; m < 2; ++m) {
+            const int L = m ? D3D_PIPEM_L : D3D_PIPEF_L;
+            const int nprod = m ? D3D_PIPEM_NPW : D3D_PIPEF_NA + D3D_PIPEF_NP;
+            const int maxt = m ? D3D_PIPEM_MAXT : D3D_PIPEF_MAXT;
+            const int ng = pb.fw + L + 1;
             const int nww = (ng * zl + 31) / 32;
-            c->pipe_threads = (nww + c->pipe_NA + c->pipe_NP + D3D_PIPE_NX + PIPE_NR + 1) * 32;   // (+ reducer) + decision warp
-            c->pipe_smem = pipe_smem_bytes<D3D_PIPE_L>(pb.fw, c->ne ? c->ne : 7, pb.kd_n, pb.Dp,
-                                                       c->pipe_NA + c->pipe_NP, ng, zl, pb.var_is_cube != 0);
+            c->pipe_threads[m] = (nww + nprod + D3D_PIPE_NX + PIPE_NR + 1) * 32;   // (+ reducer) + decision warp
+            c->pipe_smem[m] = (m ? pipe_smem_bytes<D3D_PIPEM_L> : pipe_smem_bytes<D3D_PIPEF_L>)(
+                pb.fw, c->ne ? c->ne : 7, pb.kd_n, pb.Dp, nprod, ng, zl, pb.var_is_cube != 0);
             // needs runs to pipeline along; Dp <= 64: one producer lane per channel pair, the cross
             // terms of a site in two registers per lane; <= 16 window warps: one record row
-            c->use_pipe = c->use_slide && c->pipe_threads <= D3D_PIPE_MAXT && c->pipe_smem <= 227 * 1024 &&
-                          nww <= 16 && pb.Dp <= 64 && c->mean_run >= 4.0;
-            if (const char* e = getenv("D3D_PIPE")) c->use_pipe = c->use_pipe && atoi(e) != 0;
+            c->use_pipe[m] = c->use_slide && c->pipe_threads[m] <= maxt && c->pipe_smem[m] <= 227 * 1024 &&
+                             nww <= 16 && pb.Dp <= 64 && c->mean_run >= 4.0;
+            if (const char* e = getenv("D3D_PIPE")) c->use_pipe[m] = c->use_pipe[m] && atoi(e) != 0;
         }
     }
     c->sweep_smem = smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double);
@@ -1062,40 +1088,46 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             c->launches++;
             c->pb.gtab = g;
         }
-        // the pipelined kernel walks the ROW-MAJOR list (runs of consecutive sites); the
-        // colour-ordered list of the chain-per-CTA coloured mode has no runs: sliding-window kernel
-        // Measured (profiles/r02_notes.md): the pipelined kernel is 1.4x faster per chain while
-        // the chip is partly filled (0.50 M vs 0.36 M evals/s for one chain), but its larger
-        // per-site instruction footprint costs more than the pipelining gains once every SM runs
-        // a chain (42 M vs 52 M evals/s at 148+ chains): it takes the launches of up to 3/4 SMs.
+        // The pipelined kernel walks the ROW-MAJOR list (runs of consecutive sites); the
+        // colour-ordered list of the chain-per-CTA coloured mode has no runs: sliding-window kernel.
+        // Which instantiation: per-site producers while the chip is partly filled, the batched
+        // producer once (nearly) every SM runs a chain (profiles/r02_notes.md: cycles per site
+        // 3 154 vs 4 663 for one chain, 6 322 vs 4 807 at 148; the sliding-window kernel 5 547).
+        // D3D_PIPE=0: sliding-window kernel, 2: pipelined wherever it can run (the default),
+        // 3 / 4: force the per-site / the batched instantiation.
         int sms_ = 148;
         cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, c->device);
-        bool few = c->pb.n_chains <= (3 * sms_) / 4;
-        if (const char* e = getenv("D3D_PIPE")) few = atoi(e) >= 2 ? true : few;   // D3D_PIPE=2: always
-        const bool pipe = c->use_pipe && few && c->pb.sites == c->d_sites_row;
+        int pm = c->pb.n_chains <= (D3D_PIPE_FEW_NUM * sms_) / D3D_PIPE_FEW_DEN ? 0 : 1;
+        if (const char* e = getenv("D3D_PIPE")) { if (atoi(e) == 3) pm = 0; else if (atoi(e) == 4) pm = 1; }
+        if (!c->use_pipe[pm]) pm ^= 1;
+        const bool pipe = c->use_pipe[pm] && c->pb.sites == c->d_sites_row;
         if (pipe && !c->pb.xtab) {                              // static cross-term tables, once per problem
             double* xt = nullptr;
-            const size_t n = (size_t)c->pb.n_cubes * c->pipe_L * c->pb.max_sites * c->pb.Dp;
+            const size_t n = (size_t)c->pb.n_cubes * D3D_PIPE_LMAX * c->pb.max_sites * c->pb.Dp;
             if (dalloc(c, &xt, n * sizeof(double))) return cudaErrorMemoryAllocation;
-            dim3 grid(c->pb.max_sites, c->pipe_L, c->pb.n_cubes);
-            xtab_kernel<T, IV><<<grid, 64, 0, c->stream>>>(c->pb, c->pipe_L, c->d_run_start, xt);
+            dim3 grid(c->pb.max_sites, D3D_PIPE_LMAX, c->pb.n_cubes);
+            xtab_kernel<T, IV><<<grid, 64, 0, c->stream>>>(c->pb, D3D_PIPE_LMAX, c->d_run_start, xt);
             c->launches++;
             c->pb.xtab = xt;
+            c->pb.xtab_L = D3D_PIPE_LMAX;
         }
         typedef void (*SeqKern)(const Problem, long long, long long, int, double, double*, double*,
                                 long long, long long, const int4*, const int*, int, volatile long long*);
         SeqKern kern = sweep_seq_slide_kernel<T, IV, nes>;
         int threads = c->slide_threads;
         size_t smem = c->slide_smem;
-        c->last_kernel = pipe ? "sweep_seq_pipe_kernel" : "sweep_seq_slide_kernel";
+        c->last_kernel = !pipe ? "sweep_seq_slide_kernel" : pm ? "sweep_seq_pipe_kernel<batched>" : "sweep_seq_pipe_kernel<per-site>";
         if (pipe) {
             // (square FSF of the template's size: the window geometry is a compile-time constant)
-            if (c->pb.fh == nes && c->pb.fw == nes)
-                kern = sweep_seq_pipe_kernel<T, IV, nes, true, D3D_PIPE_L, D3D_PIPE_NA, D3D_PIPE_NP, D3D_PIPE_NX, D3D_PIPE_MAXT>;
+            const bool sq = c->pb.fh == nes && c->pb.fw == nes;
+            if (pm == 0)
+                kern = sq ? sweep_seq_pipe_kernel<T, IV, nes, true, D3D_PIPEF_L, D3D_PIPEF_NA, D3D_PIPEF_NP, D3D_PIPE_NX, 0, D3D_PIPEF_MAXT>
+                          : sweep_seq_pipe_kernel<T, IV, nes, false, D3D_PIPEF_L, D3D_PIPEF_NA, D3D_PIPEF_NP, D3D_PIPE_NX, 0, D3D_PIPEF_MAXT>;
             else
-                kern = sweep_seq_pipe_kernel<T, IV, nes, false, D3D_PIPE_L, D3D_PIPE_NA, D3D_PIPE_NP, D3D_PIPE_NX, D3D_PIPE_MAXT>;
-            threads = c->pipe_threads;
-            smem = c->pipe_smem;
+                kern = sq ? sweep_seq_pipe_kernel<T, IV, nes, true, D3D_PIPEM_L, D3D_PIPEM_NPW, 0, D3D_PIPE_NX, 1, D3D_PIPEM_MAXT>
+                          : sweep_seq_pipe_kernel<T, IV, nes, false, D3D_PIPEM_L, D3D_PIPEM_NPW, 0, D3D_PIPE_NX, 1, D3D_PIPEM_MAXT>;
+            threads = c->pipe_threads[pm];
+            smem = c->pipe_smem[pm];
         }
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // balance chains over the SMs (McNaughton wrap-around of the chain x sweep rectangle)

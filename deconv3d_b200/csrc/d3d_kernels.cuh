@@ -52,7 +52,8 @@ struct Problem {
     const double* gtab;        // [cube][H*W][Dp] sum of F^2/sigma^2 over the window of a site (d3d_slide.cuh), or NULL
     const int* run_start;      // [cube][max_sites] index of the first site of the run a list entry belongs to (d3d_pipe.cuh), or NULL
     const int* run_last;       // [cube][max_sites] index of the last site of that run, or NULL
-    const double* xtab;        // [cube][L][max_sites][Dp] cross terms of consecutive sites (d3d_pipe.cuh), or NULL
+    const double* xtab;        // [cube][xtab_L][max_sites][Dp] cross terms of consecutive sites (d3d_pipe.cuh), or NULL
+    int xtab_L;                // look-ahead distances the table holds (>= the L of the kernel reading it)
     const double* kcirc;       // [P] circular LSF kernel (lib/convolution.py:89-160 in direct form)
     const double* ktap_v;      // [ntaps] values and
     const int* ktap_m;         // [ntaps] offsets m of the taps with |K[m]| >= 1e-18 max|K|

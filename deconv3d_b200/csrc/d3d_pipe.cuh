@@ -28,8 +28,9 @@
 //      [x-fhw-L, x+fhw+1] x fh rows in registers (1/sigma^2 of the same band sits in shared
 //      memory, staged with cp.async).  Step k: move the band, sums h0_k -> partial products with
 //      the profiles of k -> PART[k]; then the update of site k-L once its decision is there.
-//   A  accept uniform, first truncated-normal draws, old profile      } several warps each,
-//   P  proposal (Philox, Cauchy jump), new profile -> PROF[k]          } site k -> warp k mod N
+//   A, P  producers -> PROF[k]: draws (Philox), Cauchy jumps, accept uniform, first truncated-normal
+//      tries, old and new line profiles; either one warp per site and kind (PMODE 0) or ONE warp
+//      preparing EIGHT sites per pass, lane-parallel over the sites (PMODE 1)
 //   X  quadratic sums over the static G table + the 4L brackets -> SCAL[k]
 //   B  the serial scalar chain: totals + corrections, accept test, Gibbs draw -> DEC[k]
 // FREE[k] (W after update k, X after its last use of the profiles of k) recycles a stage.
@@ -49,7 +50,8 @@ enum { PB_PROF = 0, PB_SCAL, PB_PART, PB_DEC, PB_FREE, PB_HSUM, PB_N };
 #else
 #define PIPE_NR 0
 #endif
-#define PIPE_R 8                       // stages of the ring (> L + 2)
+#define PIPE_R 16                      // stages of the ring: two batches of PIPE_B sites of the producers
+#define PIPE_B 8                       // sites a producer warp prepares per pass (lane-parallel over the sites)
 #define PIPE_TIMEOUT 6000000000LL      // cycles (~3 s): a stalled wait aborts the launch, never hangs
 
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -152,7 +154,9 @@ template <int L> struct PipeFix {
 struct PipeVar {           // offsets (doubles) from PipeFix::VAR
     int Ft;        // [fw][NE+1]     FSF transposed: a column is contiguous (16-byte pairs)
     int Kd;        // [kd_n padded]  dense window of the circular LSF kernel (host: pb.kdense)
-    int G;         // [NA+NP][GN]    per producer warp: periodically extended Gaussian profile
+    int G;         // [NA+NP][2 PIPE_B][GN]  per producer warp and (site of the batch, old|new): periodically extended Gaussian
+    int S;         // [NA+NP][256]   per producer warp: scratch of a batch (uniforms, tan, log, normals, parameters)
+    int T64;       // [64]           2^(j/64) for exp_neg_tab
     int Lu_o;      // [R][Dp]
     int Lu_n;      // [R][Dp]
     int iv;        // [NG][NE][ZL]   16-byte vectors of 1/sigma^2 of the resident band
@@ -168,11 +172,13 @@ __host__ __device__ inline PipeVar pipe_var_layout(int fw, int NE, int kd_n, int
     v.Ft = o; o += fw * (NE + 1); o = (o + 1) & ~1;
     v.Kd = o; o += kdp;
     v.GN = (Dp + kdp + 2 + 1) & ~1;
-    v.G = o; o += nprod * v.GN;
+    v.G = o; o += nprod * 2 * PIPE_B * v.GN;     // (per-site producers use the first GN of each warp's block)
+    v.S = o; o += nprod * 256;
+    v.T64 = o; o += 64;
     v.Lu_o = o; o += PIPE_R * Dp; o = (o + 1) & ~1;
     v.Lu_n = o; o += PIPE_R * Dp; o = (o + 1) & ~1;
     v.iv = o; o += NG * NE * ZL * 2;            // (a scalar variance fills the same ring)
-    v.hs = o; o += PIPE_HS * NG * Dp;
+    v.hs = o; o += PIPE_NR * PIPE_HS * NG * Dp;
     v.total = o;
     return v;
 }
@@ -358,7 +364,7 @@ struct PipeArgs {
         __syncthreads();                                                                         \
     }                                                                                            \
     (void)alive; PP_FLUSH()
-#define PIPE_TMPL template <typename T, bool IVCUBE, int NE, bool SQ, int L, int NA, int NP, int NX>
+#define PIPE_TMPL template <typename T, bool IVCUBE, int NE, bool SQ, int L, int NA, int NP, int NX, int PMODE>
 // Measured (profiles/r02_notes.md): as separate functions the roles reach the kernel parameters
 // through a generic pointer and run ~12 % slower; inlined is the default.
 #ifdef D3D_PIPE_NOINLINE_ROLES
@@ -752,7 +758,7 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_X(PIPE_ROLE_PARAMS) {
         const int zq0 = lane < Dp ? lane : 0, zq1 = lane + 32 < Dp ? lane + 32 : 0;
         const double m0 = lane < Dp ? 1.0 : 0.0, m1 = lane + 32 < Dp ? 1.0 : 0.0;
         const double* const gt0 = pb.gtab + (size_t)cube * HW * Dp;
-        const double* const xt0 = pb.xtab + (size_t)cube * L * pb.max_sites * Dp;
+        const double* const xt0 = pb.xtab + (size_t)cube * pb.xtab_L * pb.max_sites * Dp;
         const int xstride = pb.max_sites * Dp;
         for (int j = warp - wX0; j < ns; j += NX) {
             if (*abort_flag) break;
@@ -842,13 +848,16 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_X(PIPE_ROLE_PARAMS) {
     return gbase;
 }
 
-// ---- A / P: draws, proposal and the two line profiles
+// ---- A / P: per-site producers (PMODE = 0): site k -> warp k mod NA (accept uniform, first
+// truncated-normal tries, old profile) and warp k mod NP (proposal, new profile).  Their code runs
+// every site and stays warm in the instruction caches: the fastest producers while the chip is
+// partly filled (0.62 M evals/s for one chain), four warps' worth of instruction fetch when it is not.
 PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_AP(PIPE_ROLE_PARAMS) {
     PIPE_ROLE_DECLS;
     PIPE_SWEEPS_BEGIN
         // =================================================================================
         const int pw = roleA ? warp - wA0 : NA + (warp - wP0);        // producer index
-        double* const G = s_var + pv.G + pw * pv.GN;
+        double* const G = s_var + pv.G + pw * 2 * PIPE_B * pv.GN;
         const int kd_n = pb.kd_n, kd_mhi = pb.kd_mhi, P = pb.P, D = pb.D;
         for (int j = roleA ? warp - wA0 : warp - wP0; j < ns; j += (roleA ? NA : NP)) {
             if (*abort_flag) break;
@@ -979,7 +988,192 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_AP(PIPE_ROLE_PARAMS) {
     return gbase;
 }
 
-template <typename T, bool IVCUBE, int NE, bool SQ, int L, int NA, int NP, int NX, int MAXT>
+// ---- PR: batched producers (PMODE = 1).  A warp prepares PIPE_B = 8 consecutive sites per
+// pass, lane-parallel OVER THE SITES: one Philox call gives the 8 x 4 blocks of draws, one tan()
+// the 24 Cauchy jumps, two log(), one sqrt(), one cos() the accept uniforms and the first
+// truncated-normal tries, and the 16 line profiles (old and new) are evaluated four lanes per
+// profile.  ~350 warp instructions per site instead of ~1 100 with one warp per site and role.
+// Its code runs once per 8 sites and is instruction-cache cold every time (~39 k cycles per
+// batch, profiles/r02_notes.md): the right trade when every SM runs a chain -- the per-site
+// producers above, warm but four warps, when the chip is partly filled.  Values are exchanged
+// through a 2 KB scratch of the warp.  Same draws and arithmetic per site as d3d_slide.cuh (the
+// Gaussian through the table-driven exp of the spectral pass, <= 2 ulp).  A warp's next use of a
+// stage lies one lap of the ring later (PIPE_B * warps <= PIPE_R), behind FREE.
+PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
+    PIPE_ROLE_DECLS;
+    const int NPW = NA + NP;
+    static_assert(PIPE_B * (NA + NP) <= PIPE_R && PIPE_R % (PIPE_B * (NA + NP)) == 0,
+                  "every producer warp must find its own previous batch in the stages it re-uses");
+    const int pw = warp - wA0;
+    double* const Gw = s_var + pv.G + pw * 2 * PIPE_B * pv.GN;
+    double* const sc = s_var + pv.S + pw * 256;
+    double* const sU = sc;            // [8][8]  uniforms 0..7 of every site of the batch
+    double* const sT = sc + 64;       // [8][4]  tan of the three jump uniforms
+    double* const sL = sc + 96;       // [8][8]  the five logs
+    double* const sN = sc + 160;      // [8][2]  the two pre-evaluated normals
+    double* const sP = sc + 176;      // [8][8]  a, c_old, w_old, a_new, c_new, w_new
+    const double* const tab64 = s_var + pv.T64;
+    const int kd_n = pb.kd_n, kd_mhi = pb.kd_mhi, P = pb.P, D = pb.D, GN = pv.GN;
+    const int QC = 2 * ((Dp + 7) / 8);                  // channels per lane of a profile (even)
+    const int nb = (ns + PIPE_B - 1) / PIPE_B;
+    PIPE_SWEEPS_BEGIN
+        for (int b = pw; b < nb; b += NPW) {
+            if (*abort_flag) break;
+            const int j0 = b * PIPE_B;
+            const int j = j0;                            // (named by the wait diagnostics)
+            if (lane == 0) s_prog[warp] = j0;
+            // ---- lanes 0..7: one site each -- stage recycled?, parameters ----------------------
+            const int js = j0 + (lane & 7);
+            const bool mine = lane < PIPE_B && js < ns;
+            const unsigned gjs = gbase + (unsigned)js;
+            const int st_s = (int)(gjs & (R - 1));
+            if (mine && gjs >= (unsigned)R) MWAIT(s_bar + PB_FREE * R + st_s, ((gjs / R) & 1u) ^ 1u, 7);
+            __syncwarp();
+            {
+                // Philox: lane = (site of the batch) * 4 + block; draws (2 blk, 2 blk + 1)
+                const int s4 = lane >> 2, blk = lane & 3;
+                const int jq = j0 + s4;
+                const int site_q = jq < ns ? sites[jq] : 0;
+                unsigned o[4];
+                philox_block_rolled((unsigned)pb.seed, (unsigned)(pb.seed >> 32), (unsigned)blk,
+                                    (unsigned)site_q, (unsigned)it, pb.first_chain + (unsigned)chain, o);
+                sU[s4 * 8 + 2 * blk] = Philox::u53(o[0], o[1]);
+                sU[s4 * 8 + 2 * blk + 1] = Philox::u53(o[2], o[3]);
+                if (mine) {
+                    const double* prm = pb.params + ((size_t)chain * HW + sites[js]) * 3;
+                    sP[lane * 8 + 0] = prm[0]; sP[lane * 8 + 1] = prm[1]; sP[lane * 8 + 2] = prm[2];
+                }
+            }
+            __syncwarp();
+            {
+                // Cauchy jumps (lib/run.py:570-579): lane = site * 3 + parameter, one tan() for all
+                const double q4 = 1.5707963267948966;
+                const int s3 = lane / 3, k3 = lane - 3 * s3;
+                const double u = lane < 3 * PIPE_B ? sU[s3 * 8 + k3] : 0.5;
+                const double tv = tan(-q4 + (q4 - (-q4)) * u);
+                if (lane < 3 * PIPE_B) sT[s3 * 4 + k3] = tv;
+                // accept uniform + first truncated-normal draws: five logs per site, two passes of
+                // four sites (lib/run.py:435; lib/rtnorm.py:121-122, 129)
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int s5 = pass * 4 + lane / 5, k5 = lane - 5 * (lane / 5);
+                    const bool on5 = lane < 20;
+                    const double* uu = sU + (on5 ? s5 : 0) * 8;
+                    const double u4 = uu[4];
+                    const double r4 = 1e-15 + (1.0 - 1e-15) * u4, r5 = 1e-15 + (1.0 - 1e-15) * uu[5];
+                    const double larg = k5 == 0 ? uu[3] : k5 == 1 ? r5 : k5 == 2 ? 1.0 + r4 * -1.0
+                                      : k5 == 3 ? 1.0 - u4 : 1.0 - uu[6];
+                    const double lv = log(larg);
+                    if (on5) sL[s5 * 8 + k5] = lv;
+                }
+            }
+            __syncwarp();
+            {
+                // the two normals of the Gaussian-proposal branch: lane = site * 2 + k
+                const int s2 = (lane >> 1) & 7, k2 = lane & 1;
+                const double sv = sqrt(-2.0 * sL[s2 * 8 + 3 + k2]);
+                const double cv = cos(6.283185307179586 * sU[s2 * 8 + 5 + 2 * k2]);
+                if (lane < 2 * PIPE_B) sN[s2 * 2 + k2] = sv * cv;
+            }
+            __syncwarp();
+            if (mine) {
+                // proposal, bounds (lib/run.py:374-388) and the records of this site's stage
+                const double* pp = sP + lane * 8;
+                const double a = pp[0], c_old = pp[1], w_old = pp[2];
+                const double t0 = sT[lane * 4 + 0], t1 = sT[lane * 4 + 1], t2 = sT[lane * 4 + 2];
+                const double a_new = pb.jump[0] != 0.0 ? a + pb.jump[0] * t0 : a;
+                const double c_new = c_old + pb.jump[1] * t1;
+                const double w_new = w_old + pb.jump[2] * t2;
+                const double* lo = pb.pmin + cube * 3;
+                const double* hi = pb.pmax + cube * 3;
+                const int oob = (a_new < lo[0]) | (c_new < lo[1]) | (w_new < lo[2]) |
+                                (a_new > hi[0]) | (c_new > hi[1]) | (w_new > hi[2]);
+                sP[lane * 8 + 3] = a_new; sP[lane * 8 + 4] = c_new; sP[lane * 8 + 5] = w_new;
+                double* prop_s = s_prop + st_s * 8;
+                prop_s[0] = a; prop_s[1] = c_old; prop_s[2] = w_old;
+                prop_s[3] = a_new; prop_s[4] = c_new; prop_s[5] = w_new;
+                prop_s[7] = (double)oob;
+                const double* uu = sU + lane * 8;
+                const double* ll = sL + lane * 8;
+                double* spec_s = s_spec + st_s * 16;
+                spec_s[SP_U4] = uu[4]; spec_s[SP_U5] = uu[5]; spec_s[SP_U6] = uu[6]; spec_s[SP_U7] = uu[7];
+                spec_s[SP_E1] = -ll[1]; spec_s[SP_Z1] = ll[2];
+                spec_s[SP_N1] = sN[lane * 2]; spec_s[SP_N2] = sN[lane * 2 + 1];
+                spec_s[SP_LOGU] = ll[0];
+            }
+            __syncwarp();
+            // ---- unit line profiles Lu = lsf (*) exp(-(z-c)^2 / (2 w^2)), old and new, of the 8
+            // sites: lane = site * 4 + quarter of the channels (lib/line_models.py:98-109,
+            // lib/convolution.py:89-160 in direct form).  The Gaussian goes to its G buffer
+            // periodically extended (G[i] = g[(i - mhi) mod P]), which turns the circular kernel
+            // into a dense FIR window: out[z] = sum_t Kd[t] G[z + t]  (Kd: host, d3d_set_problem).
+            {
+                const int s4 = lane >> 2, qd = lane & 3;
+                const int jq = j0 + s4;
+                const bool onq = jq < ns;
+                const int st_q = (int)((gbase + (unsigned)jq) & (R - 1));
+                const int zlo = qd * QC, zhi = min(zlo + QC, Dp);
+#pragma unroll 1
+                for (int which = 0; which < 2; ++which) {
+                    const double c_prof = sP[s4 * 8 + (which ? 4 : 1)], w_prof = sP[s4 * 8 + (which ? 5 : 2)];
+                    const double inv2w2 = 1.0 / (2.0 * (w_prof * w_prof));
+                    double* const G = Gw + (s4 * 2 + which) * GN;
+                    double* const Lu_out = s_var + (which ? pv.Lu_n : pv.Lu_o) + st_q * Dp;
+                    if (onq) {
+#pragma unroll 1
+                        for (int z = zlo; z < zhi; ++z) {
+                            const double d0 = (double)z - c_prof;
+                            double gv = 0.0;
+                            if (z < D) {
+                                gv = exp_neg_tab(-1.0 * (d0 * d0) * inv2w2, tab64);
+                                if (pb.n_comp > 1) gv += extra_components(pb, d0, inv2w2);   // tied multiplet
+                            }
+                            if (pb.has_lsf) {
+                                if (z < D) {
+#pragma unroll
+                                    for (int k = -1; k <= 2; ++k) {
+                                        const int i0 = z + kd_mhi + k * P;
+                                        if (i0 >= 0 && i0 < GN) G[i0] = gv;
+                                    }
+                                }
+                            } else {
+                                Lu_out[z] = gv;                      // lib/run.py:675-676
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (onq && pb.has_lsf) {
+                        const double2* kp = (const double2*)(s_var + pv.Kd);
+                        const int npair = (kd_n + 1) >> 1;           // Kd is zero-padded
+#pragma unroll 1
+                        for (int z = zlo; z < zhi; z += 2) {
+                            const double2* gp = (const double2*)(G + z);   // 16-byte aligned: z even
+                            double o0a = 0.0, o0b = 0.0, o1a = 0.0, o1b = 0.0;
+                            double2 gc = gp[0];
+#pragma unroll 2
+                            for (int q = 0; q < npair; ++q) {
+                                const double2 kk = kp[q];
+                                const double2 gn = gp[q + 1];
+                                o0a = fma(kk.x, gc.x, o0a);
+                                o0b = fma(kk.y, gc.y, o0b);
+                                o1a = fma(kk.x, gc.y, o1a);
+                                o1b = fma(kk.y, gn.x, o1b);
+                                gc = gn;
+                            }
+                            Lu_out[z] = z < D ? o0a + o0b : 0.0;
+                            Lu_out[z + 1] = z + 1 < D ? o1a + o1b : 0.0;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (mine) mbar_arrive(s_bar + PB_PROF * R + st_s);
+        }
+    PIPE_SWEEPS_END;
+    return gbase;
+}
+
+template <typename T, bool IVCUBE, int NE, bool SQ, int L, int NA, int NP, int NX, int PMODE, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
 sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, long long it1_all,
                       int keep, double min_rate, double* chain_out, double* lik_out,
@@ -1012,7 +1206,9 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
         s_var[pv.Ft + q] = i < fh ? pb.fsf[i * fw + dx] : 0.0;
     }
     for (int q = tid; q < pv.G - pv.Kd; q += blockDim.x) s_var[pv.Kd + q] = q < pb.kd_n ? pb.kdense[q] : 0.0;
-    for (int q = tid; q < (NA + NP) * pv.GN; q += blockDim.x) s_var[pv.G + q] = 0.0;
+    for (int q = tid; q < (NA + NP) * 2 * PIPE_B * pv.GN; q += blockDim.x) s_var[pv.G + q] = 0.0;
+    for (int q = tid; q < (NA + NP) * 256; q += blockDim.x) s_var[pv.S + q] = 0.0;
+    for (int q = tid; q < 64; q += blockDim.x) s_var[pv.T64 + q] = exp2((double)q * (1.0 / 64.0));
     for (int q = tid; q < 4002; q += blockDim.x) smem_raw[FX::TX + q] = pb.rt.x[q];
     for (int q = tid; q < 4001; q += blockDim.x) smem_raw[FX::TYU + q] = pb.rt.yu[q];
     for (int q = tid; q < 8961; q += blockDim.x)
@@ -1032,7 +1228,7 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
 #else
             const int n_part = nww;
 #endif
-            mbar_init(s_bar + q, kind == PB_PROF ? 2 : kind == PB_HSUM ? nww : kind == PB_PART ? n_part
+            mbar_init(s_bar + q, kind == PB_PROF ? (PMODE ? 1 : 2) : kind == PB_HSUM ? nww : kind == PB_PART ? n_part
                                  : kind == PB_FREE ? nww + (L + 1) : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1062,11 +1258,14 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
         if (tid == 0) s_bc[2] = (double)pb.accepted[chain];
         __syncthreads();
         // every role runs all sweeps of the item and returns the advanced site count
-        if (warp < nww)       gbase = pipe_role_W<T, IVCUBE, NE, SQ, L, NA, NP, NX>(pb, *s_args, chain, it0, it1, gbase);
-        else if (warp == wB)  gbase = pipe_role_B<T, IVCUBE, NE, SQ, L, NA, NP, NX>(pb, *s_args, chain, it0, it1, gbase);
-        else if (PIPE_NR && warp == wR) gbase = pipe_role_R<T, IVCUBE, NE, SQ, L, NA, NP, NX>(pb, *s_args, chain, it0, it1, gbase);
-        else if (warp >= wX0) gbase = pipe_role_X<T, IVCUBE, NE, SQ, L, NA, NP, NX>(pb, *s_args, chain, it0, it1, gbase);
-        else if (warp >= wA0) gbase = pipe_role_AP<T, IVCUBE, NE, SQ, L, NA, NP, NX>(pb, *s_args, chain, it0, it1, gbase);
+        if (warp < nww)       gbase = pipe_role_W<T, IVCUBE, NE, SQ, L, NA, NP, NX, PMODE>(pb, *s_args, chain, it0, it1, gbase);
+        else if (warp == wB)  gbase = pipe_role_B<T, IVCUBE, NE, SQ, L, NA, NP, NX, PMODE>(pb, *s_args, chain, it0, it1, gbase);
+        else if (PIPE_NR && warp == wR) gbase = pipe_role_R<T, IVCUBE, NE, SQ, L, NA, NP, NX, PMODE>(pb, *s_args, chain, it0, it1, gbase);
+        else if (warp >= wX0) gbase = pipe_role_X<T, IVCUBE, NE, SQ, L, NA, NP, NX, PMODE>(pb, *s_args, chain, it0, it1, gbase);
+        else if (warp >= wA0) {
+            if constexpr (PMODE != 0) gbase = pipe_role_PR<T, IVCUBE, NE, SQ, L, NA, NP, NX, PMODE>(pb, *s_args, chain, it0, it1, gbase);
+            else                      gbase = pipe_role_AP<T, IVCUBE, NE, SQ, L, NA, NP, NX, PMODE>(pb, *s_args, chain, it0, it1, gbase);
+        }
         if (items) {                                   // hand the chain over to its next owner
             __threadfence();
             __syncthreads();

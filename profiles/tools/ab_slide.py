@@ -43,7 +43,7 @@ def child(lib, chains, workload, sweeps):
             prof(None, 1)
         _, _, ms = ctx.sweep(1 + sweeps, sweeps, refresh_every=0, min_acceptance_rate=0.0)
     except Exception as e:                                  # noqa: BLE001
-        print('%-40s chains %4d  ERROR %s' % (os.path.basename(lib), chains, str(e)[:100]))
+        print('%-40s chains %4d  ERROR %s' % (os.path.basename(lib), chains, str(e)[:400]))
         return
     n_units = wl['n_cubes'] * wl['chains_per_cube']
     slots = -(-n_units // 148) if n_units > 148 else 1      # chain slots per SM (balanced launch)

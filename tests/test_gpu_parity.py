@@ -480,13 +480,13 @@ def test_multi_cube_galaxies(nat):
         assert np.array_equal(ch[:, 1:], chain[2 * i:2 * i + 2, 1:])
 
 
-@pytest.mark.parametrize('pipe', ['0', '2'])
+@pytest.mark.parametrize('pipe', ['0', '3', '4'])
 def test_balanced_schedule_more_chains_than_sms(nat, monkeypatch, pipe):
     """More chains than SMs: the chain x sweep rectangle is laid over the SMs by the
     wrap-around rule and some chains are handed from one CTA to another mid-call.  Every
     chain must still equal its own single-chain run bit for bit -- with either sweep kernel
-    (D3D_PIPE=0 sliding-window, D3D_PIPE=2 pipelined; by default the library picks by chain
-    count, and two different kernels agree to rounding, not to the bit)."""
+    (D3D_PIPE=0 sliding-window, 3 / 4 pipelined with per-site / batched producers; by default
+    the library picks by chain count, and two different kernels agree to rounding, not to the bit)."""
     monkeypatch.setenv('D3D_PIPE', pipe)
     g = load_golden('ref_run_A')
     data, fsf, lsf = g['data'], g['fsf'], g['lsf']
