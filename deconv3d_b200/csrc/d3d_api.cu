@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <math.h>
+#include <cstring>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -24,11 +25,11 @@ using namespace d3d;
 
 // pipelined sweep kernel (d3d_pipe.cuh): look-ahead, producer warps and thread bound of the
 // instantiation that ships; -D overrides are for the A/B builds of profiles/tools
-// Two instantiations of the pipelined sweep (d3d_pipe.cuh; measured in profiles/r02_notes.md):
-//   "few"  (chains <= 2/5 of the SMs): per-site producer warps (2 + 2), look-ahead 2, 16 warps at cfg2.
-//          Fastest per chain (0.62 M evals/s for one chain) while the chip is partly filled.
-//   "many": ONE batched producer warp (8 sites per pass), look-ahead 1, 13 warps at cfg2.  The
-//          smallest per-site instruction footprint: 59.8 M evals/s with every SM busy.
+// The pipelined sweep (d3d_pipe.cuh; measured in profiles/r02_notes.md) ships with BATCHED producers:
+// two producer warps, each preparing 8 sites per pass, a ring of 32 stages, look-ahead 2 -- 14 warps
+// at cfg2.  Faster than one warp per site and role at every chain count (cycles per site 2 979 vs
+// 3 209 for one chain, 4 420 vs 6 180 with every SM busy).  The per-site producers ("few" below)
+// are kept for A/B builds only: -DD3D_PIPE_PERSITE compiles them and D3D_PIPE=3 selects them.
 #ifndef D3D_PIPE_LMAX
 #define D3D_PIPE_LMAX 2         // the cross-term tables are built for this look-ahead
 #endif
@@ -45,23 +46,18 @@ using namespace d3d;
 #define D3D_PIPEF_MAXT 512      // 16 warps at cfg2: 128 registers per thread
 #endif
 #ifndef D3D_PIPEM_L
-#define D3D_PIPEM_L 1
+#define D3D_PIPEM_L 2
 #endif
 #ifndef D3D_PIPEM_NPW
-#define D3D_PIPEM_NPW 1
+#define D3D_PIPEM_NPW 2
 #endif
 #ifndef D3D_PIPEM_MAXT
-#define D3D_PIPEM_MAXT 416      // 13 warps at cfg2: 152 registers per thread
+#define D3D_PIPEM_MAXT 448      // 14 warps at cfg2: 128 registers per thread
 #endif
 #ifndef D3D_PIPE_NX
 #define D3D_PIPE_NX 1
 #endif
-// chains up to which the per-site producers win: 2/5 of the SMs (A/B on 148 SMs, cycles per site:
-// 37 chains 3 751 vs 4 712, 74 chains 5 043 vs 4 722 -- the curves cross near 60)
-#ifndef D3D_PIPE_FEW_NUM
-#define D3D_PIPE_FEW_NUM 2
-#define D3D_PIPE_FEW_DEN 5
-#endif
+
 
 static thread_local std::string g_last_error;
 
@@ -201,6 +197,7 @@ struct d3d_ctx {
     double* d_rec_stage = nullptr; size_t rec_stage_cap = 0;   // staging of host-side record buffers
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
+    bool lu_tried = false;               // the profile cache of the pipelined sweep was asked for (it is optional)
     const char* last_kernel = "";        // name of the sweep kernel of the latest d3d_sweep (bench reporting)
     int64_t window_voxels_per_sweep = 0;   // sum over cubes of sum_sites wh*ww*D * chains_per_cube
     std::vector<int> h_nsites;
@@ -224,6 +221,7 @@ static void free_problem(d3d_ctx* c) {
     c->d_lines = nullptr;
     c->pb.gtab = nullptr;
     c->pb.xtab = nullptr;
+    c->pb.lucache = nullptr; c->pb.lu_valid = 0; c->lu_tried = false;
     c->pb.run_start = nullptr;
     c->pb.run_last = nullptr;
     c->d_sites_row = nullptr; c->d_run_start = nullptr;
@@ -646,6 +644,7 @@ static int reset_chain_control(d3d_ctx* c) {
 }
 
 extern "C" int d3d_set_line_model(d3d_ctx* c, int n_components, const double* offsets, const double* ratios) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_set_line_model before d3d_set_problem");
     if (n_components < 1 || n_components > 4)
         return fail(D3D_EINVAL, "d3d_set_line_model: 1 to 4 tied Gaussian components are supported");
@@ -697,6 +696,7 @@ extern "C" int d3d_set_rng(d3d_ctx* c, uint64_t seed, uint32_t first_chain_id) {
 }
 
 extern "C" int d3d_set_params(d3d_ctx* c, const double* params) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_set_params before d3d_set_problem");
     if (!params) return fail(D3D_EINVAL, "params is NULL");
     CK(cudaSetDevice(c->device));
@@ -718,6 +718,7 @@ extern "C" int d3d_get_params(d3d_ctx* c, double* params) {
 }
 
 extern "C" int d3d_init_params_uniform(d3d_ctx* c) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem) return fail(D3D_ESTATE, "d3d_init_params_uniform before d3d_set_problem");
     CK(cudaSetDevice(c->device));
     const Problem& pb = c->pb;
@@ -1090,16 +1091,11 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
         }
         // The pipelined kernel walks the ROW-MAJOR list (runs of consecutive sites); the
         // colour-ordered list of the chain-per-CTA coloured mode has no runs: sliding-window kernel.
-        // Which instantiation: per-site producers while the chip is partly filled, the batched
-        // producer once (nearly) every SM runs a chain (profiles/r02_notes.md: cycles per site
-        // 3 154 vs 4 663 for one chain, 6 322 vs 4 807 at 148; the sliding-window kernel 5 547).
-        // D3D_PIPE=0: sliding-window kernel, 2: pipelined wherever it can run (the default),
-        // 3 / 4: force the per-site / the batched instantiation.
-        int sms_ = 148;
-        cudaDeviceGetAttribute(&sms_, cudaDevAttrMultiProcessorCount, c->device);
-        int pm = c->pb.n_chains <= (D3D_PIPE_FEW_NUM * sms_) / D3D_PIPE_FEW_DEN ? 0 : 1;
-        if (const char* e = getenv("D3D_PIPE")) { if (atoi(e) == 3) pm = 0; else if (atoi(e) == 4) pm = 1; }
-        if (!c->use_pipe[pm]) pm ^= 1;
+        // D3D_PIPE=0 forces the sliding-window kernel (A/B runs, tests of that kernel).
+        int pm = 1;
+#ifdef D3D_PIPE_PERSITE
+        if (const char* e = getenv("D3D_PIPE")) { if (atoi(e) == 3) pm = 0; }
+#endif
         const bool pipe = c->use_pipe[pm] && c->pb.sites == c->d_sites_row;
         if (pipe && !c->pb.xtab) {                              // static cross-term tables, once per problem
             double* xt = nullptr;
@@ -1111,19 +1107,33 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             c->pb.xtab = xt;
             c->pb.xtab_L = D3D_PIPE_LMAX;
         }
+        if (pipe && !c->lu_tried && !getenv("D3D_NO_LUCACHE")) {
+            // cache of the unit profile every site ended its last visit with: the next sweep's
+            // "old" profile (half of the producers' work).  Optional: without memory for it the
+            // kernel recomputes both profiles as before.
+            c->lu_tried = true;
+            void* q = nullptr;
+            const size_t bytes = (size_t)c->pb.n_chains * c->pb.H * c->pb.W * c->pb.Dp * sizeof(double);
+            if (dev_malloc(&q, bytes) == cudaSuccess) { c->allocs.push_back(q); c->pb.lucache = (double*)q; }
+            else cudaGetLastError();
+            c->pb.lu_valid = 0;
+        }
+        if (!pipe) c->pb.lu_valid = 0;                          // another kernel moves the parameters
         typedef void (*SeqKern)(const Problem, long long, long long, int, double, double*, double*,
                                 long long, long long, const int4*, const int*, int, volatile long long*);
         SeqKern kern = sweep_seq_slide_kernel<T, IV, nes>;
         int threads = c->slide_threads;
         size_t smem = c->slide_smem;
-        c->last_kernel = !pipe ? "sweep_seq_slide_kernel" : pm ? "sweep_seq_pipe_kernel<batched>" : "sweep_seq_pipe_kernel<per-site>";
+        c->last_kernel = !pipe ? "sweep_seq_slide_kernel" : pm ? "sweep_seq_pipe_kernel" : "sweep_seq_pipe_kernel<per-site>";
         if (pipe) {
             // (square FSF of the template's size: the window geometry is a compile-time constant)
             const bool sq = c->pb.fh == nes && c->pb.fw == nes;
+#ifdef D3D_PIPE_PERSITE
             if (pm == 0)
                 kern = sq ? sweep_seq_pipe_kernel<T, IV, nes, true, D3D_PIPEF_L, D3D_PIPEF_NA, D3D_PIPEF_NP, D3D_PIPE_NX, 0, D3D_PIPEF_MAXT>
                           : sweep_seq_pipe_kernel<T, IV, nes, false, D3D_PIPEF_L, D3D_PIPEF_NA, D3D_PIPEF_NP, D3D_PIPE_NX, 0, D3D_PIPEF_MAXT>;
             else
+#endif
                 kern = sq ? sweep_seq_pipe_kernel<T, IV, nes, true, D3D_PIPEM_L, D3D_PIPEM_NPW, 0, D3D_PIPE_NX, 1, D3D_PIPEM_MAXT>
                           : sweep_seq_pipe_kernel<T, IV, nes, false, D3D_PIPEM_L, D3D_PIPEM_NPW, 0, D3D_PIPE_NX, 1, D3D_PIPEM_MAXT>;
             threads = c->pipe_threads[pm];
@@ -1215,6 +1225,9 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
             c->pb, it0, it1, keep, min_rate, chain_dev, lik_dev, row_first, rows_local);
     }
     c->launches++;
+    // the pipelined kernel leaves its profile cache in step with the parameter map; any other
+    // kernel moves the parameters without it
+    c->pb.lu_valid = (strcmp(c->last_kernel, "sweep_seq_pipe_kernel") == 0 && c->pb.lucache && it1 > it0) ? 1 : 0;
     return cudaGetLastError();
 }
 
@@ -1370,6 +1383,7 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
                          lik_dev, row_first, rows_local);
             c->pb.sites = row_major;
         } else {
+            c->pb.lu_valid = 0;
             for (long long k = it; k < seg_end && e == cudaSuccess; ++k) {
                 sweep_begin_kernel<<<(pb.n_chains + 127) / 128, 128, 0, c->stream>>>(pb, k, min_acceptance_rate);
                 c->launches++;
@@ -1460,6 +1474,11 @@ extern "C" int d3d_debug_pipe_prof(unsigned long long* out512, int reset) {
     if (reset) { static unsigned long long z[32 * 16]; cudaMemcpyToSymbol(d3d::g_pipe_prof, z, sizeof z); }
     return 0;
 }
+extern "C" int d3d_debug_pipe_cta(unsigned long long* out2048) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out2048, d3d::g_pipe_cta, 2048 * sizeof(unsigned long long));
+    return 0;
+}
 #endif
 
 #ifdef D3D_PHASE_TIMING
@@ -1519,6 +1538,7 @@ extern "C" int d3d_tile_record_slots(d3d_ctx* c, int64_t* n_records) {
 }
 
 extern "C" int d3d_colour_begin(d3d_ctx* c, int64_t iteration, double min_acceptance_rate) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem || !c->have_params) return fail(D3D_ESTATE, "d3d_colour_begin needs a problem and parameters");
     CK(cudaSetDevice(c->device));
     const Problem& pb = c->pb;
@@ -1529,6 +1549,7 @@ extern "C" int d3d_colour_begin(d3d_ctx* c, int64_t iteration, double min_accept
 }
 
 extern "C" int d3d_colour_phase(d3d_ctx* c, int64_t iteration, int cy, int cx, double* records_out) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem || !c->have_params)
         return fail(D3D_ESTATE, "d3d_colour_phase needs d3d_set_problem and parameters (+ d3d_forward)");
     if (!c->have_tables) return fail(D3D_ESTATE, "d3d_colour_phase needs d3d_set_rtnorm_tables");
@@ -1559,6 +1580,7 @@ extern "C" int d3d_colour_phase(d3d_ctx* c, int64_t iteration, int cy, int cx, d
 }
 
 extern "C" int d3d_apply_records(d3d_ctx* c, const double* records, int64_t n_records) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem || !c->have_params) return fail(D3D_ESTATE, "d3d_apply_records needs a problem and parameters");
     const Problem& pb = c->pb;
     if (!pb.lik_cur) return fail(D3D_ESTATE, "d3d_apply_records needs d3d_set_tile");
@@ -1686,6 +1708,7 @@ extern "C" int d3d_tile_fused_connect(d3d_ctx* c, int index, void* peer_box, con
 }
 
 extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int cx, int64_t phase_index) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->have_problem || !c->have_params || !c->have_tables)
         return fail(D3D_ESTATE, "d3d_colour_phase_fused needs a problem, parameters and the rtnorm tables");
     if (!c->box) return fail(D3D_ESTATE, "d3d_colour_phase_fused needs d3d_tile_fused_init");
@@ -1736,6 +1759,7 @@ extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int
 }
 
 extern "C" int d3d_sweep_fused(d3d_ctx* c, int64_t first_iteration, int64_t n_iterations, double min_acceptance_rate) {
+    if (c) c->pb.lu_valid = 0;            // (profile cache of the pipelined sweep: parameters move)
     if (!c || !c->box) return fail(D3D_ESTATE, "d3d_sweep_fused needs d3d_tile_fused_init");
     if (first_iteration < 1 || n_iterations < 0) return fail(D3D_EINVAL, "bad iteration range");
     const Problem& pb = c->pb;

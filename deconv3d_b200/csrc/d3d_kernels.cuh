@@ -54,6 +54,8 @@ struct Problem {
     const int* run_last;       // [cube][max_sites] index of the last site of that run, or NULL
     const double* xtab;        // [cube][xtab_L][max_sites][Dp] cross terms of consecutive sites (d3d_pipe.cuh), or NULL
     int xtab_L;                // look-ahead distances the table holds (>= the L of the kernel reading it)
+    double* lucache;           // [chain][H*W][Dp] unit line profile every site ended its last visit with (d3d_pipe.cuh), or NULL
+    int lu_valid;              // the cache matches the parameter map at the start of this launch
     const double* kcirc;       // [P] circular LSF kernel (lib/convolution.py:89-160 in direct form)
     const double* ktap_v;      // [ntaps] values and
     const int* ktap_m;         // [ntaps] offsets m of the taps with |K[m]| >= 1e-18 max|K|

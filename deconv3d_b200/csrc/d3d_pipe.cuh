@@ -43,14 +43,16 @@
 
 namespace d3d {
 
-enum { PB_PROF = 0, PB_SCAL, PB_PART, PB_DEC, PB_FREE, PB_HSUM, PB_N };
+enum { PB_PROF = 0, PB_SCAL, PB_PART, PB_DEC, PB_FREE, PB_HSUM, PB_GO /* [0]: lock step of the producer warps */, PB_N };
 #define PIPE_HS 4                      // stages of the ring of raw window sums (> L + 1)
 #ifdef D3D_PIPE_RROLE
 #define PIPE_NR 1                      // a reducer warp between the window warps and warp B (measured slower: off)
 #else
 #define PIPE_NR 0
 #endif
-#define PIPE_R 16                      // stages of the ring: two batches of PIPE_B sites of the producers
+#ifndef PIPE_R
+#define PIPE_R 32                      // stages of the ring: two batches of PIPE_B sites of each of the two producer warps
+#endif
 #define PIPE_B 8                       // sites a producer warp prepares per pass (lane-parallel over the sites)
 #define PIPE_TIMEOUT 6000000000LL      // cycles (~3 s): a stalled wait aborts the launch, never hangs
 
@@ -99,6 +101,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // Debug build only (profiles/tools/ab_slide.py): per-warp cycle accounting of CTA 0 -- slot 0 the
 // cycles spent inside the sweeps, slot c the cycles spent in the waits with code c.
 __device__ unsigned long long g_pipe_prof[32 * 16];
+__device__ unsigned long long g_pipe_cta[1024 * 2];      // per CTA: cycles inside the kernel, SM id
 #define PP_DECL unsigned long long pp_[16]; for (int q_ = 0; q_ < 16; ++q_) pp_[q_] = 0ull
 #define MWAIT(b, par, code)                                                     \
     do { const unsigned long long t_ = clock64(); mbar_wait(b, par, abort_flag, (code) | (j << 8)); \
@@ -154,7 +157,7 @@ template <int L> struct PipeFix {
 struct PipeVar {           // offsets (doubles) from PipeFix::VAR
     int Ft;        // [fw][NE+1]     FSF transposed: a column is contiguous (16-byte pairs)
     int Kd;        // [kd_n padded]  dense window of the circular LSF kernel (host: pb.kdense)
-    int G;         // [NA+NP][2 PIPE_B][GN]  per producer warp and (site of the batch, old|new): periodically extended Gaussian
+    int G;         // [NA+NP][PIPE_B][GN]  per producer warp and site of the batch: periodically extended Gaussian (old, then new)
     int S;         // [NA+NP][256]   per producer warp: scratch of a batch (uniforms, tan, log, normals, parameters)
     int T64;       // [64]           2^(j/64) for exp_neg_tab
     int Lu_o;      // [R][Dp]
@@ -172,7 +175,7 @@ __host__ __device__ inline PipeVar pipe_var_layout(int fw, int NE, int kd_n, int
     v.Ft = o; o += fw * (NE + 1); o = (o + 1) & ~1;
     v.Kd = o; o += kdp;
     v.GN = (Dp + kdp + 2 + 1) & ~1;
-    v.G = o; o += nprod * 2 * PIPE_B * v.GN;     // (per-site producers use the first GN of each warp's block)
+    v.G = o; o += nprod * PIPE_B * v.GN;     // (per-site producers use the first GN of each warp's block)
     v.S = o; o += nprod * 256;
     v.T64 = o; o += 64;
     v.Lu_o = o; o += PIPE_R * Dp; o = (o + 1) & ~1;
@@ -287,6 +290,7 @@ struct PipeArgs {
     double min_rate;
     double* chain_out; double* lik_out;
     long long row_first, rows_local;
+    long long it_first;            // first sweep of this launch (the profile cache is good from the second on)
 };
 
 // Every role is its own __noinline__ function: ptxas then allocates registers role by role (the
@@ -857,7 +861,7 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_AP(PIPE_ROLE_PARAMS) {
     PIPE_SWEEPS_BEGIN
         // =================================================================================
         const int pw = roleA ? warp - wA0 : NA + (warp - wP0);        // producer index
-        double* const G = s_var + pv.G + pw * 2 * PIPE_B * pv.GN;
+        double* const G = s_var + pv.G + pw * PIPE_B * pv.GN;
         const int kd_n = pb.kd_n, kd_mhi = pb.kd_mhi, P = pb.P, D = pb.D;
         for (int j = roleA ? warp - wA0 : warp - wP0; j < ns; j += (roleA ? NA : NP)) {
             if (*abort_flag) break;
@@ -1005,7 +1009,7 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
     static_assert(PIPE_B * (NA + NP) <= PIPE_R && PIPE_R % (PIPE_B * (NA + NP)) == 0,
                   "every producer warp must find its own previous batch in the stages it re-uses");
     const int pw = warp - wA0;
-    double* const Gw = s_var + pv.G + pw * 2 * PIPE_B * pv.GN;
+    double* const Gw = s_var + pv.G + pw * PIPE_B * pv.GN;
     double* const sc = s_var + pv.S + pw * 256;
     double* const sU = sc;            // [8][8]  uniforms 0..7 of every site of the batch
     double* const sT = sc + 64;       // [8][4]  tan of the three jump uniforms
@@ -1016,19 +1020,31 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
     const int kd_n = pb.kd_n, kd_mhi = pb.kd_mhi, P = pb.P, D = pb.D, GN = pv.GN;
     const int QC = 2 * ((Dp + 7) / 8);                  // channels per lane of a profile (even)
     const int nb = (ns + PIPE_B - 1) / PIPE_B;
+    // The producer warps run the SAME code on consecutive batches AT THE SAME TIME: this code is
+    // instruction-cache cold at every pass (26 KB, once per 8 sites), and the fetches beyond the
+    // SM's own cache go to the L1.5 of the GPC, which all its SMs share and which saturates when
+    // every SM runs a chain (ncu gcc__*: profiles/r02_notes.md).  In lock step the second warp
+    // finds the lines the first one has just fetched.  GO[0] is their two-party barrier; its
+    // phase count `go` carries over sweeps and work items in shared memory.
+    unsigned go = (unsigned)s_bc[4];
     PIPE_SWEEPS_BEGIN
-        for (int b = pw; b < nb; b += NPW) {
+        for (int b0 = 0; b0 < nb; b0 += NPW) {
             if (*abort_flag) break;
+            const int b = b0 + pw;
             const int j0 = b * PIPE_B;
             const int j = j0;                            // (named by the wait diagnostics)
+            if (NPW > 1) {
+                if (lane == 0) mbar_arrive(s_bar + PB_GO * R);
+                MWAIT(s_bar + PB_GO * R, go & 1u, 8);
+                ++go;
+            }
+            if (b >= nb) continue;
             if (lane == 0) s_prog[warp] = j0;
-            // ---- lanes 0..7: one site each -- stage recycled?, parameters ----------------------
+            // ---- lanes 0..7: one site each (stage, parameters) ------------------------------------
             const int js = j0 + (lane & 7);
             const bool mine = lane < PIPE_B && js < ns;
             const unsigned gjs = gbase + (unsigned)js;
             const int st_s = (int)(gjs & (R - 1));
-            if (mine && gjs >= (unsigned)R) MWAIT(s_bar + PB_FREE * R + st_s, ((gjs / R) & 1u) ^ 1u, 7);
-            __syncwarp();
             {
                 // Philox: lane = (site of the batch) * 4 + block; draws (2 blk, 2 blk + 1)
                 const int s4 = lane >> 2, blk = lane & 3;
@@ -1075,7 +1091,29 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                 const double cv = cos(6.283185307179586 * sU[s2 * 8 + 5 + 2 * k2]);
                 if (lane < 2 * PIPE_B) sN[s2 * 2 + k2] = sv * cv;
             }
+            // Everything up to here lives in the warp's own scratch: only now must the stages of the
+            // batch be free again (the draws of a pass overlap the consumers' last sites of the
+            // half of the ring it refills).
+            if (mine && gjs >= (unsigned)R) MWAIT(s_bar + PB_FREE * R + st_s, ((gjs / R) & 1u) ^ 1u, 7);
             __syncwarp();
+            if (pb.lucache) {
+                // Profile cache: the site that held a stage one lap ago is done with it -- the unit
+                // profile it ENDED with (new if accepted, old if not) is its "old" profile of the
+                // next sweep (lib/run.py:402 recomputes it from the same (c, w): same bits).
+                // lane = site of the batch * 4 + quarter of the channels.
+                const int s4 = lane >> 2, qd = lane & 3;
+                const int jq = j0 + s4, jp = jq - R;
+                if (jq < ns && jp >= 0) {
+                    const int st_q = (int)((gbase + (unsigned)jq) & (R - 1));
+                    const int zlo = qd * QC, zhi = min(zlo + QC, Dp);
+                    const bool accp = s_dec[st_q * 4] != 0.0;
+                    const double2* src = (const double2*)(s_var + (accp ? pv.Lu_n : pv.Lu_o) + st_q * Dp + zlo);
+                    double2* dst = (double2*)(pb.lucache + ((size_t)chain * HW + sites[jp]) * Dp + zlo);
+#pragma unroll 1
+                    for (int q = 0; 2 * q < zhi - zlo; ++q) dst[q] = src[q];
+                }
+                __syncwarp();
+            }
             if (mine) {
                 // proposal, bounds (lib/run.py:374-388) and the records of this site's stage
                 const double* pp = sP + lane * 8;
@@ -1113,11 +1151,20 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                 const bool onq = jq < ns;
                 const int st_q = (int)((gbase + (unsigned)jq) & (R - 1));
                 const int zlo = qd * QC, zhi = min(zlo + QC, Dp);
+                // OLD profile: kept from the site's last visit (W writes it back with the outcome),
+                // unless this is the first sweep after the parameters were set from outside
+                const bool cached = pb.lucache != nullptr && (pb.lu_valid || it > ka.it_first);
+                if (cached && onq) {
+                    const double2* src = (const double2*)(pb.lucache + ((size_t)chain * HW + sites[jq]) * Dp + zlo);
+                    double2* dst = (double2*)(s_var + pv.Lu_o + st_q * Dp + zlo);
 #pragma unroll 1
-                for (int which = 0; which < 2; ++which) {
+                    for (int q = 0; 2 * q < zhi - zlo; ++q) dst[q] = src[q];
+                }
+#pragma unroll 1
+                for (int which = cached ? 1 : 0; which < 2; ++which) {
                     const double c_prof = sP[s4 * 8 + (which ? 4 : 1)], w_prof = sP[s4 * 8 + (which ? 5 : 2)];
                     const double inv2w2 = 1.0 / (2.0 * (w_prof * w_prof));
-                    double* const G = Gw + (s4 * 2 + which) * GN;
+                    double* const G = Gw + s4 * GN;
                     double* const Lu_out = s_var + (which ? pv.Lu_n : pv.Lu_o) + st_q * Dp;
                     if (onq) {
 #pragma unroll 1
@@ -1164,12 +1211,34 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                             Lu_out[z + 1] = z + 1 < D ? o1a + o1b : 0.0;
                         }
                     }
+                    __syncwarp();                                    // G is re-used by the new profile
                 }
             }
-            __syncwarp();
             if (mine) mbar_arrive(s_bar + PB_PROF * R + st_s);
         }
+        if (pb.lucache && !*abort_flag) {
+            // end of the sweep: the sites still in the ring go to the profile cache as they finish
+            for (int t = pw; t < R / PIPE_B; t += NPW) {
+                const int s4 = lane >> 2, qd = lane & 3;
+                const int jf = ns - R + t * PIPE_B + s4;
+                const int j = jf;                            // (named by the wait diagnostics)
+                if (jf >= 0) {
+                    const unsigned gjf = gbase + (unsigned)jf;
+                    const int st_q = (int)(gjf & (R - 1));
+                    // (decided is enough: only the producers write profiles, and FREE of the last
+                    // L sites completes in the next sweep)
+                    MWAIT(s_bar + PB_DEC * R + st_q, (gjf / R) & 1u, 9);
+                    const int zlo = qd * QC, zhi = min(zlo + QC, Dp);
+                    const bool accp = s_dec[st_q * 4] != 0.0;
+                    const double2* src = (const double2*)(s_var + (accp ? pv.Lu_n : pv.Lu_o) + st_q * Dp + zlo);
+                    double2* dst = (double2*)(pb.lucache + ((size_t)chain * HW + sites[jf]) * Dp + zlo);
+#pragma unroll 1
+                    for (int q = 0; 2 * q < zhi - zlo; ++q) dst[q] = src[q];
+                }
+            }
+        }
     PIPE_SWEEPS_END;
+    if (pw == 0 && lane == 0) s_bc[4] = (double)go;      // (items are separated by CTA barriers)
     return gbase;
 }
 
@@ -1196,6 +1265,9 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
     unsigned long long* const s_bar = (unsigned long long*)(smem_raw + FX::BAR);
     volatile int* const abort_flag = (volatile int*)(smem_raw + FX::ABORT);
     PipeArgs* const s_args = (PipeArgs*)(smem_raw + FX::ARGS);
+#ifdef D3D_PIPE_PROF
+    const long long t_kernel0 = clock64();
+#endif
     const int tid = threadIdx.x, warp = tid >> 5;
     const int nwt = NG * ZL, nww = (nwt + 31) >> 5;
     const int wA0 = nww, wX0 = nww + NA + NP, wR = wX0 + NX, wB = wR + PIPE_NR;
@@ -1206,7 +1278,7 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
         s_var[pv.Ft + q] = i < fh ? pb.fsf[i * fw + dx] : 0.0;
     }
     for (int q = tid; q < pv.G - pv.Kd; q += blockDim.x) s_var[pv.Kd + q] = q < pb.kd_n ? pb.kdense[q] : 0.0;
-    for (int q = tid; q < (NA + NP) * 2 * PIPE_B * pv.GN; q += blockDim.x) s_var[pv.G + q] = 0.0;
+    for (int q = tid; q < (NA + NP) * PIPE_B * pv.GN; q += blockDim.x) s_var[pv.G + q] = 0.0;
     for (int q = tid; q < (NA + NP) * 256; q += blockDim.x) s_var[pv.S + q] = 0.0;
     for (int q = tid; q < 64; q += blockDim.x) s_var[pv.T64 + q] = exp2((double)q * (1.0 / 64.0));
     for (int q = tid; q < 4002; q += blockDim.x) smem_raw[FX::TX + q] = pb.rt.x[q];
@@ -1216,8 +1288,10 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
     for (int q = tid; q < PIPE_R * 32; q += blockDim.x) smem_raw[FX::RED + q] = 0.0;
     if (tid == 0) {
         *abort_flag = 0;
+        s_bc[4] = 0.0;
         s_args->keep = keep; s_args->min_rate = min_rate; s_args->chain_out = chain_out;
         s_args->lik_out = lik_out; s_args->row_first = row_first; s_args->rows_local = rows_local;
+        s_args->it_first = it0_all;
         // The barriers are initialised ONCE: stage and phase parity follow a running count of the
         // sites this CTA has worked (gbase + j), which carries on across sweeps and work items, so
         // every phase is completed by the sites that follow (no re-initialisation in flight).
@@ -1229,7 +1303,7 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
             const int n_part = nww;
 #endif
             mbar_init(s_bar + q, kind == PB_PROF ? (PMODE ? 1 : 2) : kind == PB_HSUM ? nww : kind == PB_PART ? n_part
-                                 : kind == PB_FREE ? nww + (L + 1) : 1);
+                                 : kind == PB_FREE ? nww + (L + 1) : kind == PB_GO ? NA + NP : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1272,6 +1346,14 @@ sweep_seq_pipe_kernel(const __grid_constant__ Problem pb, long long it0_all, lon
             if (tid == 0) progress[chain] = it1;
         }
     }
+#ifdef D3D_PIPE_PROF
+    if (tid == 0 && blockIdx.x < 1024) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_pipe_cta[blockIdx.x * 2] = clock64() - t_kernel0;
+        g_pipe_cta[blockIdx.x * 2 + 1] = smid;
+    }
+#endif
 }
 
 }  // namespace d3d

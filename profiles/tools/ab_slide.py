@@ -64,6 +64,15 @@ def child(lib, chains, workload, sweeps):
             if a[w, 0] == 0:
                 continue
             print('   warp %2d ' % w + ' '.join('%8.0f' % (a[w, k] / per_site) for k in range(14)))
+        if hasattr(lib_h, 'd3d_debug_pipe_cta') and n_units <= 148:
+            cb = (ctypes.c_ulonglong * 2048)()
+            lib_h.d3d_debug_pipe_cta(cb)
+            c = np.array(cb[:], dtype=np.float64).reshape(1024, 2)[:n_units]
+            cyc = c[:, 0] / (sweeps * n_sites)
+            order = np.argsort(cyc)
+            print('   per-CTA cycles per site (whole kernel): min %.0f  median %.0f  max %.0f' %
+                  (cyc.min(), np.median(cyc), cyc.max()))
+            print('   (cycles, smid) sorted: ' + ' '.join('%.0f@%d' % (cyc[i], int(c[i, 1])) for i in order))
 
 
 if __name__ == '__main__':

@@ -480,13 +480,13 @@ def test_multi_cube_galaxies(nat):
         assert np.array_equal(ch[:, 1:], chain[2 * i:2 * i + 2, 1:])
 
 
-@pytest.mark.parametrize('pipe', ['0', '3', '4'])
+@pytest.mark.parametrize('pipe', ['0', '1'])
 def test_balanced_schedule_more_chains_than_sms(nat, monkeypatch, pipe):
     """More chains than SMs: the chain x sweep rectangle is laid over the SMs by the
     wrap-around rule and some chains are handed from one CTA to another mid-call.  Every
     chain must still equal its own single-chain run bit for bit -- with either sweep kernel
-    (D3D_PIPE=0 sliding-window, 3 / 4 pipelined with per-site / batched producers; by default
-    the library picks by chain count, and two different kernels agree to rounding, not to the bit)."""
+    (D3D_PIPE=0 sliding-window, 1 pipelined; two different kernels agree to rounding, not to
+    the bit)."""
     monkeypatch.setenv('D3D_PIPE', pipe)
     g = load_golden('ref_run_A')
     data, fsf, lsf = g['data'], g['fsf'], g['lsf']
@@ -511,6 +511,51 @@ def test_balanced_schedule_more_chains_than_sms(nat, monkeypatch, pipe):
     # a second call continues every chain where it stopped
     acc2, its2, _ = ctx.sweep(8, 3)
     assert (its2 == 11).all() and (acc2 >= acc).all()
+
+
+def test_profile_cache_of_the_pipelined_sweep_changes_nothing(nat, monkeypatch):
+    """The pipelined kernel keeps the unit line profile every site ended its last visit with and
+    reads it back as the next sweep's OLD profile instead of recomputing it from the same (c, w)
+    (lib/run.py:402).  With the cache and without it (D3D_NO_LUCACHE=1) the chains are the same
+    to the bit -- over several calls, after set_params() between calls (cache invalid: the
+    first sweep recomputes), after a coloured sweep in between, and for chains handed over
+    between CTAs (more chains than SMs)."""
+    g = load_golden('ref_run_A')
+    data, fsf, lsf = g['data'], g['fsf'], g['lsf']
+    var = np.array([0.01])
+    n = 160
+
+    def run(no_cache):
+        if no_cache:
+            monkeypatch.setenv('D3D_NO_LUCACHE', '1')
+        else:
+            monkeypatch.delenv('D3D_NO_LUCACHE', raising=False)
+        ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=n, seed=11)
+        ctx.init_params_uniform()
+        ctx.forward(write_err=True)
+        out = []
+        chain = np.zeros((n, 13, 9, 10, 3))
+        ctx.sweep(1, 4, chain_out=chain)                     # first call: sweep 1 fills the cache
+        ctx.sweep(5, 3, chain_out=chain)                     # second call: cache valid from its first sweep
+        out.append(chain[:, 1:8].copy())
+        p = ctx.get_params()
+        p[..., 1] += 0.25                                    # parameters moved from outside
+        ctx.set_params(p)
+        ctx.forward(write_err=True)
+        ctx.sweep(8, 2, chain_out=chain)
+        ctx.sweep(10, 1, mode=nat.COLOURED, chain_out=chain)  # another kernel moves them
+        ctx.sweep(11, 2, chain_out=chain)
+        out.append(chain[:, 8:13].copy())
+        out.append(ctx.get_residual())
+        kern = ctx.last_kernel()
+        ctx.close()
+        return out, kern
+
+    a, kern = run(False)
+    b, _ = run(True)
+    assert kern.startswith('sweep_seq_pipe_kernel')
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
 
 
 def _cfg2_problem(nat, chains, dtype=None, fsf_size=13, seed=42):
