@@ -394,14 +394,6 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_W(PIPE_ROLE_PARAMS) {
     { double t_[VEC]; for (int v = 0; v < VEC; ++v) t_[v] = ivs; pack(ivs_vec, t_); }
     PIPE_SWEEPS_BEGIN
         // =================================================================================
-        // rows of the chain / likelihood arrays this sweep is saved to (lib/run.py:353);
-        // thread 0 writes them when it applies the update of a site
-        double* crow = nullptr; double* lrow = nullptr;
-        if (tid == 0 && (it % keep) == 0) {
-            const long long r = it / keep - row_first;
-            if (chain_out) crow = chain_out + ((size_t)chain * rows_local + r) * HW * 3;
-            if (lik_out) lrow = lik_out + ((size_t)chain * rows_local + r) * HW;
-        }
         int next_u = 0;                              // first site whose update is still pending
         int site = 0, x = 0, y = 0, m = 0;
         int j_last = -1;                             // last list entry of the current run
@@ -527,17 +519,6 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_W(PIPE_ROLE_PARAMS) {
                         pack(ecache[i2], e);
                     }
                 }
-                if (tid == 0) {
-                    // the outcome of site i goes to the parameter map and the saved rows
-                    // (lib/run.py:430-432, 448, 499, 516)
-                    const double* pr = s_prop + sti * 8;
-                    const int site_i = site - (j - i);
-                    const double c_end = acc ? pr[4] : pr[1], w_end = acc ? pr[5] : pr[2];
-                    double* prm = pb.params + ((size_t)chain * HW + site_i) * 3;
-                    prm[0] = r; prm[1] = c_end; prm[2] = w_end;
-                    if (crow) { double* cr = crow + (size_t)site_i * 3; cr[0] = r; cr[1] = c_end; cr[2] = w_end; }
-                    if (lrow) lrow[site_i] = dc[3];
-                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_bar + PB_FREE * R + sti);
             }
@@ -580,6 +561,14 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_B(PIPE_ROLE_PARAMS) {
 #pragma unroll
         for (int d = 0; d < L; ++d) { ha[d] = 0.0; hr[d] = 0.0; hacc[d] = false; }
         const double lo_a = pb.pmin[cube * 3], hi_a = pb.pmax[cube * 3];
+        // rows of the chain / likelihood arrays this sweep is saved to (lib/run.py:353); lane 0
+        // writes them, and the parameter map, right behind each decision
+        double* crow = nullptr; double* lrow = nullptr;
+        if ((it % keep) == 0) {
+            const long long r = it / keep - row_first;
+            if (chain_out) crow = chain_out + ((size_t)chain * rows_local + r) * HW * 3;
+            if (lik_out) lrow = lik_out + ((size_t)chain * rows_local + r) * HW;
+        }
         for (int j = 0; j < ns; ++j) {
             if (*abort_flag) break;
             if (lane == 0) s_prog[warp] = j;
@@ -676,8 +665,19 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_B(PIPE_ROLE_PARAMS) {
             const double r = rs_ * sg + mu;                                 // :82-83
             if (lane == 0) {
                 double* dc = s_dec + st * 4;
+                // (the proposal record is read before DEC is raised: the stage may be recycled
+                // as soon as the window warps have applied this decision)
+                const double* pr = s_prop + st * 8;
+                const double c_end = acc ? pr[4] : pr[1], w_end = acc ? pr[5] : pr[2];
                 dc[0] = acc ? 1.0 : 0.0; dc[1] = r; dc[2] = a; dc[3] = delta;
                 mbar_arrive(s_bar + PB_DEC * R + st);
+                // the outcome goes to the parameter map and the saved rows
+                // (lib/run.py:430-432, 448, 499, 516)
+                const int site_j = sites[j];
+                double* prm = pb.params + ((size_t)chain * HW + site_j) * 3;
+                prm[0] = r; prm[1] = c_end; prm[2] = w_end;
+                if (crow) { double* cr = crow + (size_t)site_j * 3; cr[0] = r; cr[1] = c_end; cr[2] = w_end; }
+                if (lrow) lrow[site_j] = delta;
             }
             accepted += acc;
 #pragma unroll
