@@ -558,6 +558,87 @@ def test_profile_cache_of_the_pipelined_sweep_changes_nothing(nat, monkeypatch):
         assert np.array_equal(x, y)
 
 
+FUZZ = [  # D, H, W, fh, fw, variance, masked, chains, lsf sigma (0: none), dtype
+    (16, 9, 10, 7, 7, 'cube', False, 1, 0.9, 'f64'),
+    (12, 5, 37, 5, 5, 'scalar', True, 3, 0.7, 'f64'),        # long rows, holes: runs of every length
+    (40, 14, 9, 13, 13, 'cube', True, 2, 1.1, 'f64'),         # field narrower than the stamp
+    (30, 20, 33, 11, 11, 'scalar', False, 150, 0.9, 'f64'),   # more chains than SMs: hand-over
+    (32, 8, 64, 9, 13, 'cube', True, 5, 0.0, 'f64'),          # non-square stamp, no LSF, W > ring
+    (20, 3, 70, 3, 3, 'cube', False, 2, 0.8, 'f64'),          # tiny stamp
+    (64, 10, 12, 7, 7, 'cube', False, 2, 1.0, 'f64'),         # D = 64: full wrap of the LSF
+    (24, 12, 41, 13, 13, 'cube', True, 4, 0.9, 'f32'),
+    (10, 1, 50, 7, 7, 'scalar', False, 2, 0.6, 'f64'),        # one row
+    (18, 33, 2, 5, 5, 'cube', False, 2, 0.9, 'f64'),          # two columns: runs of two
+]
+
+
+@pytest.mark.parametrize('case', range(len(FUZZ)))
+def test_pipelined_and_sliding_window_sweeps_agree(nat, monkeypatch, case):
+    """The two sequential sweep kernels are independent implementations of lib/run.py:367-519 (one
+    keeps the window sums fresh, the other corrects stale sums through the cross tables; their
+    producers evaluate exp differently): on shapes chosen to stress the pipelined kernel's
+    protocol -- runs shorter than a producer batch, fewer sites than ring stages, masks, rows
+    longer than the ring, non-square stamps, several calls -- they must take the SAME decisions
+    and end with the same chains and residuals to rounding.  Where the library does not run the
+    pipelined kernel for a shape, the case still checks the kernel that runs."""
+    D, H, W, fh, fw, vk, masked, n, sig, dt = FUZZ[case]
+    rs = np.random.RandomState(100 + case)
+    data = synthetic(D, H, W, seed=case)
+    yy, xx = np.mgrid[0:fh, 0:fw]
+    fsf = np.exp(-((yy - fh // 2) ** 2 + (xx - fw // 2) ** 2) / (2 * 1.3 ** 2)) * (1 + 0.1 * rs.rand(fh, fw))
+    fsf /= fsf.sum()
+    mid = (D - 1) // 2 - (D % 2 - 1)                     # centre of an LSF vector (lib/spread_functions.py:212-228)
+    lsf = np.zeros(D)
+    if sig > 0:
+        lsf = np.exp(-(np.arange(D) - mid) ** 2 / (2 * sig ** 2))
+        lsf[np.abs(np.arange(D) - mid) > 7] = 0.0
+        lsf /= lsf.sum()
+    else:
+        lsf[mid] = 1.0
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W)) if vk == 'cube' else np.array([0.05 ** 2])
+    mask = (rs.rand(H, W) > 0.25).astype(np.float64) if masked else None
+    dtype = nat.F32 if dt == 'f32' else nat.F64
+    out = {}
+    for pipe in ('0', '1'):
+        monkeypatch.setenv('D3D_PIPE', pipe)
+        ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, mask=mask, dtype=dtype, chains=n, seed=3 + case)
+        ctx.init_params_uniform()
+        ctx.forward(write_err=True)
+        chain = np.zeros((n, 7, H, W, 3))
+        lik = np.zeros((n, 7, H, W))
+        a1, _, _ = ctx.sweep(1, 4, chain_out=chain, lik_out=lik, min_acceptance_rate=0.0)
+        a2, i2, _ = ctx.sweep(5, 2, chain_out=chain, lik_out=lik, min_acceptance_rate=0.0)
+        out[pipe] = (chain.copy(), lik.copy(), a2.copy(), ctx.get_residual(), ctx.last_kernel())
+        assert (i2 == 7).all()
+        ctx.close()
+    c0, l0, a0, r0, k0 = out['0']
+    c1, l1, a1, r1, k1 = out['1']
+    if dt == 'f32':
+        # single precision: the kernels sum in different orders (1e-5 relative on delta-logL), a
+        # decision next to its threshold may flip and the chains then part: same statistics only
+        assert np.all(np.abs(a0 - a1) <= 0.05 * np.maximum(a0, a1) + 8), (a0, a1)
+        assert np.isfinite(c1).all() and np.isfinite(r1).all()
+        return
+    assert np.array_equal(a0, a1), (k0, k1)                    # identical accept counts
+    # centres and widths: every entry.  Amplitudes: every entry except where the line of that
+    # site is narrower than 0.05 channels -- its profile is then below 1e-40 everywhere (often
+    # denormal or zero), the site carries no flux, the amplitude is drawn from the prior alone and
+    # WHICH cell of the truncated-normal table the draw starts from hangs on the sign of a
+    # ~1e-305 number (as = -mu / sigma, lib/rtnorm.py:74-76), i.e. on how exp() rounds below
+    # 1e-300.  Nothing else depends on such an amplitude: the residuals below still agree.
+    np.testing.assert_allclose(c1[..., 1:], c0[..., 1:], rtol=1e-8, atol=1e-8)
+    flux = c0[..., 2] >= 0.05
+    np.testing.assert_allclose(c1[..., 0][flux], c0[..., 0][flux], rtol=1e-8, atol=1e-8)
+    assert flux.mean() > 0.5
+    np.testing.assert_allclose(r1, r0, rtol=0, atol=1e-9 * max(1.0, np.abs(data).max()))
+    # delta-logL of a proposal is taken at the site's CURRENT amplitude (lib/run.py:400-426): the
+    # exemption carries over to the sweep after a zero-flux visit
+    prev = np.concatenate([flux[:, :1], flux[:, :-1]], axis=1)
+    ok = flux & prev
+    scale = np.abs(l0).max() + 1.0
+    np.testing.assert_allclose(l1[ok], l0[ok], rtol=1e-6, atol=1e-9 * scale)
+
+
 def _cfg2_problem(nat, chains, dtype=None, fsf_size=13, seed=42):
     """BASELINE cfg2 at full size: 40x40x40 cube, Moffat 13x13, MUSE LSF, variance cube."""
     from deconv3d_b200 import synthetic, MUSE
