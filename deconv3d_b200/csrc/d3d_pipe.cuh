@@ -44,7 +44,9 @@
 namespace d3d {
 
 enum { PB_PROF = 0, PB_SCAL, PB_PART, PB_DEC, PB_FREE, PB_HSUM, PB_GO /* [0]: lock step of the producer warps */, PB_N };
+#ifndef PIPE_HS
 #define PIPE_HS 4                      // stages of the ring of raw window sums (> L + 1)
+#endif
 #ifdef D3D_PIPE_RROLE
 #define PIPE_NR 1                      // a reducer warp between the window warps and warp B (measured slower: off)
 #else
@@ -1038,7 +1040,10 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                 MWAIT(s_bar + PB_GO * R, go & 1u, 8);
                 ++go;
             }
-            if (b >= nb) continue;
+            if (b >= nb) {                               // (odd number of batches: still meet the partner below)
+                if (NPW > 1 && lane == 0) mbar_arrive(s_bar + PB_GO * R + 1);
+                continue;
+            }
             if (lane == 0) s_prog[warp] = j0;
             // ---- lanes 0..7: one site each (stage, parameters) ------------------------------------
             const int js = j0 + (lane & 7);
@@ -1096,6 +1101,13 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
             // half of the ring it refills).
             if (mine && gjs >= (unsigned)R) MWAIT(s_bar + PB_FREE * R + st_s, ((gjs / R) & 1u) ^ 1u, 7);
             __syncwarp();
+            if (NPW > 1) {
+                // the warps' stages come free at different times: meet again (GO[1]) so that the
+                // rest of the pass -- most of its code -- runs in lock step too.  Costs nothing
+                // while the producers are ahead: both batches are needed only a half ring later.
+                if (lane == 0) mbar_arrive(s_bar + PB_GO * R + 1);
+                MWAIT(s_bar + PB_GO * R + 1, (go - 1u) & 1u, 10);
+            }
             if (pb.lucache) {
                 // Profile cache: the site that held a stage one lap ago is done with it -- the unit
                 // profile it ENDED with (new if accepted, old if not) is its "old" profile of the
