@@ -197,6 +197,7 @@ struct d3d_ctx {
     double* d_rec_stage = nullptr; size_t rec_stage_cap = 0;   // staging of host-side record buffers
     size_t sweep_smem = 0;
     int64_t launches = 0, last_bytes = 0, last_updates = 0;
+    cudaStream_t copy_stream = nullptr;   // device->host copies of chain rows overlapping the next sweeps (d3d_sweep)
     bool lu_tried = false;               // the profile cache of the pipelined sweep was asked for (it is optional)
     const char* last_kernel = "";        // name of the sweep kernel of the latest d3d_sweep (bench reporting)
     int64_t window_voxels_per_sweep = 0;   // sum over cubes of sum_sites wh*ww*D * chains_per_cube
@@ -271,6 +272,7 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     if (c->rt_nc) dev_free(c->rt_nc);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -1303,6 +1305,8 @@ static cudaError_t launch_colour(d3d_ctx* c, long long it, double* chain_dev, do
          : (c->pb.var_is_cube ? DISPATCH_NE(FN, float, true, __VA_ARGS__)                   \
                               : DISPATCH_NE(FN, float, false, __VA_ARGS__)))
 
+static bool is_device_ptr(const void* p);
+
 extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iterations, int mode,
                          int keep_one_in, int refresh_every, double min_acceptance_rate,
                          double* chain_out, double* lik_out, int64_t n_rows,
@@ -1358,6 +1362,45 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         if (const char* ev = getenv("D3D_COLOUR_BY_CHAIN")) colour_by_chain = whole && atoi(ev) != 0;
     }
     stamp("staging alloc");
+    // rows of [r0, r1) of every chain from the staging arrays to the caller's arrays: one strided
+    // copy per array (row block of chain k -> rows [r0, r1) of chain k)
+    auto copy_rows = [&](long long r0, long long r1, cudaStream_t st) {
+        if (rc || r1 <= r0) return;
+        cudaError_t ce = cudaSuccess;
+        if (chain_dev) {
+            const size_t rb = HW * 3 * sizeof(double);
+            ce = cudaMemcpy2DAsync(chain_out + (size_t)r0 * HW * 3, (size_t)n_rows * rb,
+                                   chain_dev + (size_t)(r0 - row_first) * HW * 3, (size_t)rows_local * rb,
+                                   (size_t)(r1 - r0) * rb, pb.n_chains, cudaMemcpyDefault, st);
+            if (ce != cudaSuccess) rc = fail(D3D_ECUDA, "chain copy failed: %s", cudaGetErrorString(ce));
+        }
+        if (lik_dev && !rc) {
+            const size_t rb = HW * sizeof(double);
+            ce = cudaMemcpy2DAsync(lik_out + (size_t)r0 * HW, (size_t)n_rows * rb,
+                                   lik_dev + (size_t)(r0 - row_first) * HW, (size_t)rows_local * rb,
+                                   (size_t)(r1 - r0) * rb, pb.n_chains, cudaMemcpyDefault, st);
+            if (ce != cudaSuccess) rc = fail(D3D_ECUDA, "likelihood copy failed: %s", cudaGetErrorString(ce));
+        }
+    };
+    // Many rows going to HOST memory (the reference's default keep_one_in=1: 272 MB per call of the
+    // benched workload): the sweeps are launched in up to four chunks and the rows of a chunk travel
+    // on a second stream while the next chunk computes.  A copy to pageable memory blocks the host,
+    // so chunk i+1 is always enqueued before the copy of chunk i is started.
+    long long chunk = 0;
+    {
+        const bool to_host = (chain_dev && !is_device_ptr(chain_out)) || (lik_dev && !is_device_ptr(lik_out));
+        const double row_bytes = (double)pb.n_chains * rows_local * HW * sizeof(double) *
+                                 ((chain_dev ? 3 : 0) + (lik_dev ? 1 : 0));
+        if (to_host && mode == D3D_SEQ_EXACT && row_bytes > 64e6 && n_iterations >= 8 && !getenv("D3D_NO_COPY_OVERLAP")) {
+            chunk = (n_iterations + 3) / 4;
+            if (!c->copy_stream && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+                cudaGetLastError(); chunk = 0;
+            }
+        }
+    }
+    cudaEvent_t seg_done = nullptr;                 // end of the latest chunk whose rows still wait
+    long long pend_r0 = 0, pend_r1 = 0;             // its rows
+    if (chunk && cudaEventCreateWithFlags(&seg_done, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); chunk = 0; }
     cudaEventRecord(c->ev0, c->stream);
     cudaError_t e = cudaSuccess;
     long long it = it_begin;
@@ -1368,6 +1411,7 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
             long long next_refresh = ((it + refresh_every - 1) / refresh_every) * refresh_every;
             seg_end = std::min(it_end, next_refresh + 1);
         }
+        if (chunk) seg_end = std::min(seg_end, it + chunk);
         if (mode == D3D_SEQ_EXACT) {
             e = DISPATCH(launch_seq, c, it, seg_end, keep_one_in, min_acceptance_rate, chain_dev,
                          lik_dev, row_first, rows_local);
@@ -1394,6 +1438,18 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
         }
         if (e == cudaSuccess && refresh_every > 0 && (seg_end - 1) % refresh_every == 0)
             rc = run_forward(c, pb.params, 1, nullptr, 1, nullptr);
+        if (chunk && e == cudaSuccess && !rc) {
+            // this chunk is enqueued: the rows of the previous one may go (the host blocks in that
+            // copy while the GPU works on this chunk), then remember this chunk's rows
+            if (pend_r1 > pend_r0) {
+                cudaStreamWaitEvent(c->copy_stream, seg_done, 0);
+                copy_rows(pend_r0, pend_r1, c->copy_stream);
+                cudaStreamSynchronize(c->copy_stream);      // (the event is re-used below)
+            }
+            cudaEventRecord(seg_done, c->stream);
+            pend_r0 = (it + keep_one_in - 1) / keep_one_in;
+            pend_r1 = (seg_end - 1) / keep_one_in + 1;
+        }
         it = seg_end;
     }
     cudaEventRecord(c->ev1, c->stream);
@@ -1401,22 +1457,11 @@ extern "C" int d3d_sweep(d3d_ctx* c, int64_t first_iteration, int64_t n_iteratio
     stamp("launches enqueued");
     if (timing) { cudaStreamSynchronize(c->stream); stamp("kernels done"); }
 
-    // copy the recorded rows to the caller's [n_chains][n_rows] arrays: one strided copy per
-    // array (row block of chain k -> rows [row_first, row_first + rows_local) of chain k)
     if (!rc && rows_local > 0) {
-        if (chain_dev) {
-            const size_t w = (size_t)rows_local * HW * 3 * sizeof(double);
-            e = cudaMemcpy2DAsync(chain_out + (size_t)row_first * HW * 3, (size_t)n_rows * HW * 3 * sizeof(double),
-                                  chain_dev, w, w, pb.n_chains, cudaMemcpyDefault, c->stream);
-            if (e != cudaSuccess) rc = fail(D3D_ECUDA, "chain copy failed: %s", cudaGetErrorString(e));
-        }
-        if (lik_dev && !rc) {
-            const size_t w = (size_t)rows_local * HW * sizeof(double);
-            e = cudaMemcpy2DAsync(lik_out + (size_t)row_first * HW, (size_t)n_rows * HW * sizeof(double),
-                                  lik_dev, w, w, pb.n_chains, cudaMemcpyDefault, c->stream);
-            if (e != cudaSuccess) rc = fail(D3D_ECUDA, "likelihood copy failed: %s", cudaGetErrorString(e));
-        }
+        if (chunk) copy_rows(pend_r0, pend_r1, c->stream);               // the last chunk's rows
+        else copy_rows(row_first, row_first + rows_local, c->stream);
     }
+    if (seg_done) cudaEventDestroy(seg_done);
     std::vector<long long> h_acc(pb.n_chains), h_it(pb.n_chains);
     int h_status = 0;
     if (!rc) {

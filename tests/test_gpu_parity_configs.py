@@ -146,6 +146,25 @@ def test_cfg2x256_benched_launch_vs_oracle(nat, monkeypatch, pipe):
         _check_chain(ref, trace, chain[k], lik[k], int(acc[k]), int(its[k]), res[k], arrays['data'][0])
 
 
+def test_overlapped_row_copies_change_nothing(nat, monkeypatch):
+    """keep_one_in=1 on the benched workload sends ~100 MB of chain and likelihood rows to host
+    memory per call: d3d_sweep then launches the sweeps in chunks and copies the rows of a chunk
+    while the next one computes.  Same rows, same counters as the single launch + single copy
+    (D3D_NO_COPY_OVERLAP=1), to the bit."""
+    wl, arrays = _bench_arrays('cfg2x256', 256)
+    out = []
+    for off in ('1', None):
+        if off:
+            monkeypatch.setenv('D3D_NO_COPY_OVERLAP', off)
+        else:
+            monkeypatch.delenv('D3D_NO_COPY_OVERLAP', raising=False)
+        chain, lik, acc, its, res = _device_run(nat, arrays, 256, 10, nat.SEQ_EXACT)
+        out.append((chain, lik, acc, its, res))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert (out[1][3] == 10).all() and np.abs(out[1][0][:, 9]).max() > 0
+
+
 def test_cfg5_galaxy_vs_oracle(nat):
     """(ii) Survey batch: galaxy 2 of a 3-galaxy context (32^3, FSF 11x11, own data/variance)."""
     wl, arrays = _bench_arrays('cfg5', 3)
