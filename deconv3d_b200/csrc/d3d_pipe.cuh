@@ -28,12 +28,17 @@
 //      [x-fhw-L, x+fhw+1] x fh rows in registers (1/sigma^2 of the same band sits in shared
 //      memory, staged with cp.async).  Step k: move the band, sums h0_k -> partial products with
 //      the profiles of k -> PART[k]; then the update of site k-L once its decision is there.
-//   A, P  producers -> PROF[k]: draws (Philox), Cauchy jumps, accept uniform, first truncated-normal
-//      tries, old and new line profiles; either one warp per site and kind (PMODE 0) or ONE warp
-//      preparing EIGHT sites per pass, lane-parallel over the sites (PMODE 1)
+//   P  producers -> PROF[k]: draws (Philox), Cauchy jumps, accept uniform, first truncated-normal
+//      tries, new line profile (the old one comes from the profile cache, Problem::lucache).
+//      Shipped (PMODE 1): two warps, each preparing EIGHT sites per pass lane-parallel over the
+//      sites, in lock step (GO barriers) because their code is instruction-cache cold at every
+//      pass and the fetches go to the L1.5 all SMs of a GPC share.  PMODE 0 (one warp per site
+//      and kind) is compiled with -DD3D_PIPE_PERSITE for A/B runs only.
 //   X  quadratic sums over the static G table + the 4L brackets -> SCAL[k]
-//   B  the serial scalar chain: totals + corrections, accept test, Gibbs draw -> DEC[k]
+//   B  the serial scalar chain: totals + corrections, accept test, Gibbs draw -> DEC[k]; also
+//      writes the outcome to the parameter map and the saved chain / likelihood rows
 // FREE[k] (W after update k, X after its last use of the profiles of k) recycles a stage.
+// Measurements behind every one of these choices: profiles/r02_notes.md.
 //
 // Pipelining runs along "runs" of the site list (consecutive sites of one row, x increasing by
 // one); at the end of a run the window warps drain the pending updates, so any mask and any
