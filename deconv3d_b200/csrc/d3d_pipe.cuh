@@ -535,7 +535,11 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_W(PIPE_ROLE_PARAMS) {
             // just been applied) writes it back and takes the column that enters the WINDOW two
             // sites from now -- done here, behind the sums of this site, so that the (rarely
             // executed, instruction-cache-cold) switch never delays a decision
+#ifdef D3D_KO_SWITCH      // timing experiment only (wrong results): what the steady-state column switch costs
+            if (false)
+#else
             if (wt && !last && m == 0)
+#endif
                 pipe_switch_column<T, IVCUBE, NE>(ecache, heldX, heldY, colvalid, x + fhw + 2, y, true, fh, fhh, H, W,
                                                   Dp, zp * VEC, rstride, errT, ivT, ivs_mine, ZL, ivs_vec);
             PP_STAMP(9, pp_t);                       // [9] column switch
