@@ -1049,6 +1049,9 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                 MWAIT(s_bar + PB_GO * R, go & 1u, 8);
                 ++go;
             }
+            // OLD profiles come from the cache unless this is the first sweep after the parameters
+            // were set from outside (then they are computed, and every site is written back)
+            const bool cached = pb.lucache != nullptr && (pb.lu_valid || it > ka.it_first);
             if (b >= nb) {                               // (odd number of batches: still meet the partner below)
                 if (NPW > 1 && lane == 0) mbar_arrive(s_bar + PB_GO * R + 1);
                 continue;
@@ -1124,10 +1127,10 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                 // lane = site of the batch * 4 + quarter of the channels.
                 const int s4 = lane >> 2, qd = lane & 3;
                 const int jq = j0 + s4, jp = jq - R;
-                if (jq < ns && jp >= 0) {
+                const bool accp = jq < ns && jp >= 0 && s_dec[(int)((gbase + (unsigned)jq) & (R - 1)) * 4] != 0.0;
+                if (jq < ns && jp >= 0 && (accp || !cached)) {   // (a rejected visit leaves the cached profile as it is)
                     const int st_q = (int)((gbase + (unsigned)jq) & (R - 1));
                     const int zlo = qd * QC, zhi = min(zlo + QC, Dp);
-                    const bool accp = s_dec[st_q * 4] != 0.0;
                     const double2* src = (const double2*)(s_var + (accp ? pv.Lu_n : pv.Lu_o) + st_q * Dp + zlo);
                     double2* dst = (double2*)(pb.lucache + ((size_t)chain * HW + sites[jp]) * Dp + zlo);
 #pragma unroll 1
@@ -1172,9 +1175,7 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                 const bool onq = jq < ns;
                 const int st_q = (int)((gbase + (unsigned)jq) & (R - 1));
                 const int zlo = qd * QC, zhi = min(zlo + QC, Dp);
-                // OLD profile: kept from the site's last visit (W writes it back with the outcome),
-                // unless this is the first sweep after the parameters were set from outside
-                const bool cached = pb.lucache != nullptr && (pb.lu_valid || it > ka.it_first);
+                // OLD profile: kept from the site's last visit
                 if (cached && onq) {
                     const double2* src = (const double2*)(pb.lucache + ((size_t)chain * HW + sites[jq]) * Dp + zlo);
                     double2* dst = (double2*)(s_var + pv.Lu_o + st_q * Dp + zlo);
@@ -1239,6 +1240,7 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
         }
         if (pb.lucache && !*abort_flag) {
             // end of the sweep: the sites still in the ring go to the profile cache as they finish
+            const bool cached_sweep = pb.lu_valid || it > ka.it_first;
             for (int t = pw; t < R / PIPE_B; t += NPW) {
                 const int s4 = lane >> 2, qd = lane & 3;
                 const int jf = ns - R + t * PIPE_B + s4;
@@ -1253,8 +1255,9 @@ PIPE_TMPL PIPE_ROLE_FN unsigned pipe_role_PR(PIPE_ROLE_PARAMS) {
                     const bool accp = s_dec[st_q * 4] != 0.0;
                     const double2* src = (const double2*)(s_var + (accp ? pv.Lu_n : pv.Lu_o) + st_q * Dp + zlo);
                     double2* dst = (double2*)(pb.lucache + ((size_t)chain * HW + sites[jf]) * Dp + zlo);
+                    if (accp || !cached_sweep)
 #pragma unroll 1
-                    for (int q = 0; 2 * q < zhi - zlo; ++q) dst[q] = src[q];
+                        for (int q = 0; 2 * q < zhi - zlo; ++q) dst[q] = src[q];
                 }
             }
         }
