@@ -165,6 +165,36 @@ def test_overlapped_row_copies_change_nothing(nat, monkeypatch):
     assert (out[1][3] == 10).all() and np.abs(out[1][0][:, 9]).max() > 0
 
 
+def test_soak_benched_workload_across_refreshes(nat):
+    """1 500 sweeps of the benched workload (256 chains, balanced launch, pipelined kernel) in
+    three calls that cross the residual refresh of lib/run.py:521-534 at iteration 1000: every
+    chain reaches the last iteration, no bounded wait gives up, chi^2 per voxel settles at 1, and
+    500 sweeps after the refresh the incrementally updated residual still equals
+    data - forward(parameters) to rounding (7e8 site updates; the barrier phases of a CTA have
+    wrapped 1e5 times)."""
+    wl, arrays = _bench_arrays('cfg2x256', 256)
+    ctx = nat.Context(0, nat.F64)
+    ctx.set_rtnorm_tables(*_tables())
+    ctx.set_rng(7, 0)
+    ctx.set_problem(arrays['data'], arrays['var'], arrays['fsf'], arrays['lsf'], arrays['pmin'],
+                    arrays['pmax'], [0, 0.1, 0.1], arrays['prior'], chains_per_cube=256)
+    ctx.init_params_uniform()
+    ctx.forward(write_err=True)
+    it = 1
+    for n in (700, 650, 150):
+        acc, its, _ = ctx.sweep(it, n, refresh_every=1000, min_acceptance_rate=0.0)
+        it += n
+        assert (its == it).all()
+    res = ctx.get_residual()
+    sim = ctx.simulate(ctx.get_params())
+    data = arrays['data'][0]
+    assert np.abs((data[None] - sim) - res).max() < 1e-9 * np.abs(data).max()
+    chi2 = (res ** 2 / arrays['var'][0][None]).sum(axis=(1, 2, 3)) / data.size
+    assert 0.95 < chi2.min() and chi2.max() < 1.1
+    assert ctx.last_kernel().startswith('sweep_seq_pipe_kernel')
+    ctx.close()
+
+
 def test_cfg5_galaxy_vs_oracle(nat):
     """(ii) Survey batch: galaxy 2 of a 3-galaxy context (32^3, FSF 11x11, own data/variance)."""
     wl, arrays = _bench_arrays('cfg5', 3)
