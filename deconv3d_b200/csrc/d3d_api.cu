@@ -23,13 +23,12 @@
 
 using namespace d3d;
 
-// pipelined sweep kernel (d3d_pipe.cuh): look-ahead, producer warps and thread bound of the
-// instantiation that ships; -D overrides are for the A/B builds of profiles/tools
-// The pipelined sweep (d3d_pipe.cuh; measured in profiles/r02_notes.md) ships with BATCHED producers:
-// two producer warps, each preparing 8 sites per pass, a ring of 32 stages, look-ahead 2 -- 14 warps
-// at cfg2.  Faster than one warp per site and role at every chain count (cycles per site 2 979 vs
-// 3 209 for one chain, 4 420 vs 6 180 with every SM busy).  The per-site producers ("few" below)
-// are kept for A/B builds only: -DD3D_PIPE_PERSITE compiles them and D3D_PIPE=3 selects them.
+// The pipelined sweep (d3d_pipe.cuh; measured in profiles/r02_notes.md) ships with BATCHED producers
+// (D3D_PIPEM_*): two lock-stepped producer warps, each preparing 8 sites per pass, a ring of 32
+// stages, look-ahead 2 -- 14 warps at cfg2.  Faster than one warp per site and role at every chain
+// count.  The per-site producers (D3D_PIPEF_*) are kept for A/B builds only: -DD3D_PIPE_PERSITE
+// compiles them and D3D_PIPE=3 selects them.  Every -D override below is for the A/B builds of
+// profiles/tools/build_variant.sh.
 #ifndef D3D_PIPE_LMAX
 #define D3D_PIPE_LMAX 2         // the cross-term tables are built for this look-ahead
 #endif
@@ -180,7 +179,7 @@ struct d3d_ctx {
     bool use_slide = false; int slide_threads = 384; size_t slide_smem = 0;
     static size_t sweep_smem_base(const Problem& pb) { return smem_doubles(pb.fh, pb.fw, pb.P, pb.Dp) * sizeof(double); }   // sliding register window (seq mode)
     // pipelined sweep kernel (d3d_pipe.cuh): look-ahead L, producer warps, launch shape
-    // pipelined sweep: [0] = per-site producers (few chains), [1] = batched producer (many chains)
+    // pipelined sweep: [0] = per-site producers (A/B builds only), [1] = batched producers (shipped)
     bool use_pipe[2] = {false, false}; int pipe_threads[2] = {0, 0}; size_t pipe_smem[2] = {0, 0};
     int* d_sites_row = nullptr; int* d_run_start = nullptr; double mean_run = 0.0;
     void* d_sched = nullptr; size_t sched_cap = 0;     // work-item lists of the balanced launch
