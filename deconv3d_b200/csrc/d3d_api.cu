@@ -3,6 +3,7 @@
 // Host-side runtime of the likelihood hot path: device memory, layout
 // conversion, kernel selection and launch, segmentation of the sweep at the
 // residual-refresh points of lib/run.py:525-534, CUDA-event timing.
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -754,6 +755,35 @@ static int stencil_config(const d3d_ctx* c, int* TY, int* TX, int* ZC, size_t* s
 }
 
 
+// Tensor map (TMA descriptor) of a [n_sets][H][W][Dp] array of doubles for boxes of
+// (zc, bx, by, 1) elements; positions outside the array read as zero.  The driver's encoder is
+// looked up at run time (no link against libcuda); false when it is not there or refuses.
+static bool encode_lines_map(CUtensorMap* map, const double* base, int Dp, int W, int H, int n_sets, int zc, int bx, int by) {
+    typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Encode enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            enc = (Encode)fn;
+        else
+            cudaGetLastError();
+    }
+    if (!enc || bx > 256 || by > 256 || zc > 256 || ((size_t)Dp * sizeof(double)) % 16 || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)Dp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_sets};
+    const cuuint64_t strides[3] = {(cuuint64_t)Dp * sizeof(double), (cuuint64_t)W * Dp * sizeof(double),
+                                   (cuuint64_t)H * W * Dp * sizeof(double)};
+    const cuuint32_t box[4] = {(cuuint32_t)zc, (cuuint32_t)bx, (cuuint32_t)by, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double* sim_dev,
                        int write_err, double* chi2_dev, int n_sets = -1) {
     Problem pb = c->pb;
@@ -803,8 +833,8 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
     {
         // two output rows per thread (tile 16 x 16) while two CTAs of that tile still fit an SM
         const int TXt = 16, ZCt = 16;
-        auto tiled_smem = [&](int ty) {
-            return ((size_t)pb.fh * (pb.fw + 1) + (size_t)(ty + pb.fh - 1) * (TXt + pb.fw - 1) * ZCt) * sizeof(double);
+        auto tiled_smem = [&](int ty) {     // tile, FSF (even count), one mbarrier
+            return ((size_t)((pb.fh * (pb.fw + 1) + 1) & ~1) + (size_t)(ty + pb.fh - 1) * (TXt + pb.fw - 1) * ZCt + 2) * sizeof(double);
         };
         const int RYt = (pb.H > 8 && tiled_smem(16) <= 110 * 1024 && !getenv("D3D_STENCIL_RY1")) ? 2 : 1;
         const int TYt = 8 * RYt;
@@ -813,10 +843,21 @@ static int run_forward(d3d_ctx* c, const double* d_params, int convolve, double*
         dim3 grid_t((unsigned)(pb.n_chains * ((pb.H + TYt - 1) / TYt) * ((pb.W + TXt - 1) / TXt)),
                     (unsigned)((pb.Dp + ZCt - 1) / ZCt));
         bool launched = false;
+        // tensor map of the [set][y][x][z] array of convolved lines for the halo-tile box of this
+        // launch (host-side encoding only; falls back to the cp.async staging loop without it)
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof tmap);
+        bool tma = ok && !getenv("D3D_STENCIL_NO_TMA") &&
+                   encode_lines_map(&tmap, c->d_lines, pb.Dp, pb.W, pb.H, pb.n_chains, ZCt, TXt + pb.fw - 1, TYt + pb.fh - 1);
 #define D3D_TILED_RY(TT, FWV, RYV)                                                                  \
         {                                                                                           \
-            CK(cudaFuncSetAttribute(stencil_tiled_kernel<TT, FWV, RYV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
-            stencil_tiled_kernel<TT, FWV, RYV><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev); \
+            if (tma) {                                                                              \
+                CK(cudaFuncSetAttribute(stencil_tiled_kernel<TT, FWV, RYV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+                stencil_tiled_kernel<TT, FWV, RYV, true><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev, tmap); \
+            } else {                                                                                \
+                CK(cudaFuncSetAttribute(stencil_tiled_kernel<TT, FWV, RYV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+                stencil_tiled_kernel<TT, FWV, RYV, false><<<grid_t, 256, smem_t, c->stream>>>(pb, c->d_lines, sim_dev, write_err, chi2_dev, tmap); \
+            }                                                                                       \
         }
 #define D3D_TILED(FWV)                                                                              \
         if (ok && !launched && pb.fw == FWV) {                                                      \

@@ -19,20 +19,26 @@ template <typename T> struct Pair;
 template <> struct Pair<double> { typedef double2 P; };
 template <> struct Pair<float>  { typedef float2  P; };
 
-template <typename T, int FW, int RY>
+// TMA = true: the halo tile arrives as ONE bulk tensor copy (cp.async.bulk.tensor, a 4-D box of the
+// [set][y][x][z] array issued by one thread, completion on an mbarrier): the box may start at
+// negative coordinates and end beyond the field -- the TMA unit fills those positions with zeros,
+// which IS the 'same' border -- and the ~300 address / predicate / LDGSTS instructions per thread
+// of the staging loop disappear.  TMA = false keeps the cp.async loop (no tensor map at hand).
+template <typename T, int FW, int RY, bool TMA>
 __global__ void __launch_bounds__(256, 2)
 stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restrict__ lines,
-                     double* sim_out, int write_err, double* chi2_out) {
+                     double* sim_out, int write_err, double* chi2_out, const __grid_constant__ CUtensorMap tmap) {
     // RY output rows per thread (tile of 8*RY x 16 spaxels): a tile row loaded from shared memory
     // serves RY output rows, and the FSF row is read as 16-byte pairs (row stride FW+1), so that
     // the LDS pipe (4 cycles per LDS.128 of a warp) stays below the FP64 pipe (2 DFMA warps/cycle):
     // RY = 1: 16 tile + 13 FSF loads per 104 DFMA (13 columns); RY = 2: 16 + 14 per 208.
     const int TY = 8 * RY, TX = 16, RX = 4, ZC = 16, FWP = FW + 1;
-    extern __shared__ double smem_raw[];
+    extern __shared__ __align__(128) double smem_tile[];
     const int fh = pb.fh, Dp = pb.Dp, D = pb.D, H = pb.H, W = pb.W;
     const int hx = TX + FW - 1, hy = TY + fh - 1;
-    double* F = smem_raw;                                   // [fh][FW+1], last column 0
-    double* tile = F + fh * FWP;                            // [hy][hx][ZC], 16-byte aligned
+    double* tile = smem_tile;                               // [hy][hx][ZC]: 128-byte aligned (TMA destination)
+    double* F = tile + (size_t)hy * hx * ZC;                // [fh][FW+1], last column 0
+    unsigned long long* mbar = (unsigned long long*)(F + ((fh * FWP + 1) & ~1));
     const int ty_n = (H + TY - 1) / TY, tx_n = (W + TX - 1) / TX;
     const int chain = blockIdx.x / (ty_n * tx_n);
     const int trem = blockIdx.x - chain * ty_n * tx_n;
@@ -41,6 +47,21 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
     const int cube = chain / pb.chains_per_cube;
     const int tid = threadIdx.x;
 
+    if (TMA) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)(hy * hx * ZC * sizeof(double));
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
+            asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                         ::"r"(dst), "l"(&tmap), "r"(z0), "r"(tx0 - pb.fhw), "r"(ty0 - pb.fhh), "r"(chain), "r"(mb) : "memory");
+        }
+    }
     for (int i = tid; i < fh * FWP; i += 256) {
         const int j = i / FWP, k = i - j * FWP;
         F[i] = k < FW ? pb.fsf[j * FW + k] : 0.0;
@@ -64,6 +85,7 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
     // staging): every copy of the thread is in flight at once, so the staging phase costs about one
     // memory round trip instead of one per group of four loads (2 CTAs of 8 warps per SM cannot
     // hide them otherwise).  Positions outside the field are the zero 'same' border.
+    if (!TMA)
 #pragma unroll 4
     for (int i = tid; i < hy * hx * (ZC / 2); i += 256) {    // double2 granularity
         const int zq = i & 7, s = i >> 3;
@@ -78,8 +100,16 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
             *(double2*)dst = make_double2(0.0, 0.0);
         }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (TMA) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+        unsigned ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(mb) : "memory");
+    } else {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
 
     const int zq = tid & 7, xb = (tid >> 3) & 3, oy = tid >> 5;
