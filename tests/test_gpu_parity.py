@@ -558,6 +558,41 @@ def test_profile_cache_of_the_pipelined_sweep_changes_nothing(nat, monkeypatch):
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize('shape,fs,sets', [((40, 40, 40), 13, 3), ((30, 17, 23), 7, 2), ((12, 5, 50), 3, 1),
+                                           ((64, 9, 9), 17, 2), ((16, 33, 16), 11, 1)])
+def test_stencil_tile_by_tma_and_by_cp_async_agree(nat, monkeypatch, shape, fs, sets):
+    """The register-tiled spatial pass stages its halo tile either with one TMA tensor copy (the
+    borders of the field come from the TMA unit's zero fill of out-of-range coordinates) or with
+    the cp.async loop (explicit zero stores): same cubes and same residuals to the bit, same chi^2, for fields smaller and larger than a tile, several parameter sets, D not a multiple of
+    the 16-channel chunk, and against the oracle's forward model at 1e-12."""
+    port, _, _ = _oracle()
+    D, H, W = shape
+    rs = np.random.RandomState(D + fs)
+    fsf = port.moffat_fsf_image((fs, fs), 0.2, fwhm_arcsec=0.8, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0005 if D > 16 else 0.00025, 1.25e-4, D)
+    data = synthetic(D, H, W, 5)
+    var = 0.01 * (1 + rs.rand(D, H, W))
+    params = np.stack([np.dstack([rs.rand(H, W) * 9, rs.rand(H, W) * (D - 1), 0.3 + rs.rand(H, W) * 4])
+                       for _ in range(sets)])
+    out = []
+    for off in (None, '1'):
+        if off:
+            monkeypatch.setenv('D3D_STENCIL_NO_TMA', off)
+        else:
+            monkeypatch.delenv('D3D_STENCIL_NO_TMA', raising=False)
+        ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=sets)
+        ctx.set_params(params)
+        sim, chi = ctx.forward(want_sim=True, write_err=True, want_chi2=True)
+        out.append((sim.copy(), ctx.get_residual().copy(), np.array(chi)))
+        ctx.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-12)    # (block sums meet in atomics: order varies)
+    err_ref = port.compute_error_in_one_step(data, params[0], fsf, lsf, np.ones((H, W)))
+    scale = max(np.abs(out[0][0]).max(), np.abs(data).max())
+    np.testing.assert_allclose(out[0][1][0], err_ref, rtol=0, atol=1e-12 * scale)
+
+
 FUZZ = [  # D, H, W, fh, fw, variance, masked, chains, lsf sigma (0: none), dtype
     (16, 9, 10, 7, 7, 'cube', False, 1, 0.9, 'f64'),
     (12, 5, 37, 5, 5, 'scalar', True, 3, 0.7, 'f64'),        # long rows, holes: runs of every length
