@@ -943,8 +943,15 @@ static int forward_common(d3d_ctx* c, const double* params_any, int convolve, do
         cudaError_t e = cudaMemcpyAsync(chi2_out, d_chi, pb.n_chains * sizeof(double), cudaMemcpyDefault, c->stream);
         if (e != cudaSuccess) rc = fail(D3D_ECUDA, "chi2 copy failed: %s", cudaGetErrorString(e));
     }
+    int h_status = 0;
+    if (!rc) cudaMemcpyAsync(&h_status, pb.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (!rc && e != cudaSuccess) rc = fail(D3D_ECUDA, "forward failed: %s", cudaGetErrorString(e));
+    if (!rc && h_status == 3) {
+        cudaMemsetAsync(pb.status, 0, sizeof(int), c->stream);
+        rc = fail(D3D_ECUDA, "the spatial pass of the forward model never received a halo tile from the TMA unit; "
+                             "results of this call are invalid (D3D_STENCIL_NO_TMA=1 selects the cp.async staging)");
+    }
     if (tmp_params) dev_free(tmp_params);
     if (d_sim) dev_free(d_sim);
     if (d_chi) dev_free(d_chi);

@@ -103,9 +103,13 @@ stencil_tiled_kernel(const __grid_constant__ Problem pb, const double* __restric
     if (TMA) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
         unsigned ok = 0;
-        while (!ok)
+        const long long t0 = clock64();
+        while (!ok) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                          : "=r"(ok) : "r"(mb) : "memory");
+            // (never seen; a tile that does not arrive within ~2 s must end in an error, not in a hung GPU)
+            if (!ok && clock64() - t0 > 4000000000LL) { atomicExch(pb.status, 3); break; }
+        }
     } else {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
