@@ -45,6 +45,23 @@ REFRESH_EVERY = 1000          # lib/run.py:525: residual recomputed every 1000 i
 _CHUNK = 1000                 # iterations per native call (log line + early-exit check)
 
 
+def _host_rows(shape, zeroed):
+    """Host array for chain rows.  Page-locked (through torch's caching host allocator, so that a
+    second Run re-uses the block): the rows of a sweep travel device -> host by DMA at PCIe speed
+    while the next sweeps compute, instead of through the driver's bounce buffer into freshly
+    faulted pages (272 MB per 20 sweeps of 256 chains at the reference's keep_one_in=1).  The
+    numpy array keeps the tensor alive.  Falls back to ordinary memory when pinning fails."""
+    n = int(np.prod(shape))
+    if n * 8 >= (1 << 20) and not os.environ.get('D3D_NO_PINNED_ROWS'):
+        try:
+            import torch
+            t = (torch.zeros if zeroed else torch.empty)(shape, dtype=torch.float64, pin_memory=True)
+            return t.numpy()
+        except (RuntimeError, ImportError):
+            pass
+    return np.zeros(shape)
+
+
 class Run(object):
     """
     Deconvolves the emission-line kinematics of a hyperspectral cube.
@@ -163,8 +180,11 @@ class Run(object):
                 likelihoods = torch.zeros((n_chains, n_saved, height, width),
                                           dtype=torch.float64, device=tdev)
             else:
-                chains = np.zeros((n_chains, n_saved, height, width, n_params))
-                likelihoods = np.zeros((n_chains, n_saved, height, width))
+                # every kept row of every chain is written by the device unless a chain stops on
+                # min_acceptance_rate: only then do the arrays need the zeros of lib/run.py:270-271
+                may_stop = min_acceptance_rate > 0
+                chains = _host_rows((n_chains, n_saved, height, width, n_params), may_stop)
+                likelihoods = _host_rows((n_chains, n_saved, height, width), may_stop)
         except (MemoryError, RuntimeError):
             self.logger.error("Not enough RAM available for that many iterations. "
                               "Use a higher value in the keep_one_in= parameter.")
