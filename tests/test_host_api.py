@@ -163,3 +163,20 @@ def test_tied_gaussians_line_model_vs_oracle():
         TiedGaussiansLineModel([0, 1], [0.0, 1.0])
     with pytest.raises(ValueError):
         TiedGaussiansLineModel([0, 1, 2, 3, 4], [1, 1, 1, 1, 1])
+
+
+def test_chain_row_arrays_fall_back_to_ordinary_memory_without_a_gpu():
+    """`Run` asks for page-locked chain arrays (DMA at PCIe speed); where pinning is impossible
+    (no CUDA device, D3D_NO_PINNED_ROWS) it gets ordinary zeroed memory of the same shape."""
+    import os
+    from deconv3d_b200.run import _host_rows
+    for zeroed in (True, False):
+        a = _host_rows((2, 70, 20, 20, 3), zeroed)              # 1.3 MB: above the pinning threshold
+        assert a.shape == (2, 70, 20, 20, 3) and a.dtype == np.float64 and a.flags['C_CONTIGUOUS']
+        a[...] = 1.0                                            # writable
+    os.environ['D3D_NO_PINNED_ROWS'] = '1'
+    try:
+        assert not _host_rows((2, 70, 20, 20, 3), False).any()  # ordinary memory is always zeroed
+    finally:
+        del os.environ['D3D_NO_PINNED_ROWS']
+    assert not _host_rows((3, 4), True).any()                   # small arrays: never pinned

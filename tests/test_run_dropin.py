@@ -187,3 +187,31 @@ def test_chain_mean_entry_point_host_and_device_buffers():
     np.testing.assert_allclose(ctx.chain_mean(torch.from_numpy(chain).cuda(), 4), ref, rtol=1e-13, atol=1e-14)
     with pytest.raises(_native.NativeError):
         ctx.chain_mean(chain, 11)
+
+
+@pytest.mark.parametrize('min_rate', [0.0, 0.9])
+def test_page_locked_chain_rows_equal_ordinary_ones(monkeypatch, min_rate):
+    """``Run`` keeps the chain rows in page-locked host memory (not zeroed when no chain can stop).
+    Same chains, likelihoods and parameters as with ordinary numpy arrays, bit for bit -- also when
+    every chain stops early on min_acceptance_rate and the unwritten rows must read zero
+    (lib/run.py:270-271, 344-359), and with spaxels off the mask."""
+    from deconv3d_b200 import Run, MUSE
+    cube = _muse_cube()
+    mask = np.ones((30, 30))
+    mask[3:9, 10:20] = 0
+    out = []
+    for off in (None, '1'):
+        if off:
+            monkeypatch.setenv('D3D_NO_PINNED_ROWS', off)
+        else:
+            monkeypatch.delenv('D3D_NO_PINNED_ROWS', raising=False)
+        run = Run(cube, instrument=MUSE(), mask=mask.copy(), max_iterations=60, seed=3, n_chains=3,
+                  min_acceptance_rate=min_rate)
+        assert run.chains.nbytes > (1 << 20)                       # above the pinning threshold
+        out.append((run.chains.copy(), run.all_likelihoods.copy(), run.parameters.copy(),
+                    np.array(run.iterations_done)))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    if min_rate > 0:
+        assert (out[0][3] < 60).all()                              # the chains did stop ...
+        assert not out[0][0][:, -1, mask == 1].any()               # ... and their last rows are zeros
