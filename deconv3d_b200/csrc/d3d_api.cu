@@ -364,6 +364,20 @@ static void choose_launch(d3d_ctx* c) {
     c->apply_cluster_attr_set = false;
     // big windows: split one site over a thread-block cluster (d3d_tile.cuh)
     c->cluster = (c->ne == 0 && (long long)pb.fh * pb.fw * pb.Dp >= 32768) ? 4 : 0;
+    if (c->cluster) {
+        // A colour phase is latency-bound (one site's chain of loads, reduction, decision, update):
+        // give a site as many CTAs as still leave EVERY site of the largest class resident at once
+        // (2 CTAs of 320 threads x 96 registers per SM).  cfg4: 7 x 7 sites -> 6 CTAs per site =
+        // 294 of 296 slots, 49.6 ms per sweep instead of 57.7 with 4 (7 and 8 need a second wave:
+        // 74 ms); a 128 x 128 field (16 sites): 29.3 / 22.8 / 19.7 us per phase with 4 / 6 / 8
+        // (profiles/r02_notes.md).  Taken from the WHOLE field, not from this context's tile:
+        // the split of the window sums fixes their rounding, and tiles must reproduce one context.
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        const long long per_phase = (long long)((pb.H + pb.fh - 1) / pb.fh) * ((pb.W + pb.fw - 1) / pb.fw) * pb.n_chains;
+        const long long fit = per_phase > 0 ? (2LL * sms) / per_phase : 0;
+        if (fit > 4) c->cluster = (int)std::min<long long>(fit, 8);   // 8: the portable cluster limit
+    }
     if (const char* e = getenv("D3D_CLUSTER")) c->cluster = c->ne == 0 ? atoi(e) : 0;
     if (c->cluster < 2) c->cluster = 0;
 }
@@ -1282,7 +1296,8 @@ static cudaError_t launch_seq(d3d_ctx* c, long long it0, long long it1, int keep
 
 template <typename T, bool IV, int NE>
 static cudaError_t launch_colour_class(d3d_ctx* c, long long it, int cy, int cx, double* chain_dev,
-                                       double* lik_dev, long long rows_local, long long row_local) {
+                                       double* lik_dev, long long rows_local, long long row_local,
+                                       bool pdl = false) {
     const Problem& pb = c->pb;
     const int ne = NE ? NE : 7;
     if (!c->colour_attr_set) {
@@ -1309,10 +1324,16 @@ static cudaError_t launch_colour_class(d3d_ctx* c, long long it, int cy, int cx,
         cfg.blockDim = dim3(320);
         cfg.dynamicSmemBytes = c->sweep_smem;
         cfg.stream = c->stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        // Programmatic dependent launch between the colour phases of one sweep: the CTAs of phase
+        // p+1 are scheduled while phase p drains, set up their constants, proposal and line profiles
+        // (nothing a neighbouring phase writes) and wait (`griddepcontrol.wait`) right before their
+        // first access to the residual.  Only behind another phase kernel (`pdl`).
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
         c->launches++;
         return cudaLaunchKernelEx(&cfg, sweep_colour_cluster_kernel<T, IV>, pb, it, cy, cx, nlx, chain_dev,
                                   lik_dev, rows_local, row_local);
@@ -1332,10 +1353,14 @@ static cudaError_t launch_colour(d3d_ctx* c, long long it, double* chain_dev, do
                                  long long rows_local, long long row_local) {
     const Problem& pb = c->pb;
     cudaError_t e = cudaSuccess;
+    const bool pdl_ok = !getenv("D3D_NO_PDL");
+    bool behind_phase = false;                       // the previous launch on the stream was a phase of this sweep
     for (int cy = 0; cy < pb.fh && e == cudaSuccess; ++cy)
         for (int cx = 0; cx < pb.fw && e == cudaSuccess; ++cx) {
             if (cy >= pb.H || cx >= pb.W) continue;
-            e = launch_colour_class<T, IV, NE>(c, it, cy, cx, chain_dev, lik_dev, rows_local, row_local);
+            e = launch_colour_class<T, IV, NE>(c, it, cy, cx, chain_dev, lik_dev, rows_local, row_local,
+                                               pdl_ok && behind_phase);
+            behind_phase = true;
         }
     return e;
 }

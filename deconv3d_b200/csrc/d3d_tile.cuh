@@ -170,6 +170,9 @@ __device__ __forceinline__ void cluster_site_update(const Problem& pb, const Sme
 #pragma unroll
     for (int v = 0; v < VEC; ++v) { h[v] = 0.0; g[v] = 0.0; }
     double f2 = 0.0;
+    // everything above reads what no colour phase writes (constants, this site's own parameters,
+    // the counter-based random stream); from here on the residual of the previous phase is needed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (worker) {
         const int UN = 4;
         // (dy, dx) of the running position advance by NC without divisions
@@ -318,6 +321,9 @@ __global__ void __launch_bounds__(320)
 sweep_colour_cluster_kernel(const __grid_constant__ Problem pb, long long it, int cy, int cx, int nlx,
                             double* crow_base, double* lrow_base, long long rows_local,
                             long long row_local) {
+    // (programmatic dependent launch, see launch_colour_class: the next phase may be scheduled as soon
+    // as every CTA of this one runs; it waits in cluster_site_update before it touches the residual)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     cg::cluster_group cluster = cg::this_cluster();
     const int CS = (int)cluster.num_blocks(), cr = (int)cluster.block_rank();
     extern __shared__ double smem_raw[];

@@ -788,3 +788,44 @@ def test_tiny_field_smaller_than_fsf(nat):
     var = np.array([0.05 ** 2])      # (the default variance guess needs H > 6, lib/run.py:187)
     _compare_chain(nat, data, fsf, lsf, var, None, init, 6, 1, seed=8)
     _compare_chain(nat, data, fsf, lsf, var, None, init, 5, 1, seed=9, mode='colour')
+
+
+@pytest.mark.parametrize('cluster', [None, '4', '7'])
+def test_colour_phases_with_and_without_dependent_launch_agree(nat, monkeypatch, cluster):
+    """The phase kernels of one coloured sweep are launched as programmatic dependents
+    (`griddepcontrol.launch_dependents` / `.wait` in sweep_colour_cluster_kernel: phase p+1 sets up
+    while phase p drains and waits in front of its first residual access).  A phase that read the
+    residual too early would take other decisions: chains, likelihood rows, residual and counters
+    equal the plainly serialised launches (D3D_NO_PDL=1) to the bit over 529 phases per sweep, with
+    the cluster size the library picks and with forced ones (an odd size included)."""
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(5)
+    D, H, W = 64, 40, 44                   # 23 x 23 x 64 window: the library takes the cluster kernel by itself
+    data = synthetic(D, H, W, 13)
+    fsf = port.moffat_fsf_image((23, 23), 0.2, fwhm_arcsec=1.2, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    init = np.dstack([rs.rand(H, W) * 4, 20 + rs.rand(H, W) * 24, 0.7 + rs.rand(H, W) * 2])
+    if cluster:
+        monkeypatch.setenv('D3D_CLUSTER', cluster)
+    else:
+        monkeypatch.delenv('D3D_CLUSTER', raising=False)
+    out = []
+    for no_pdl in (None, '1'):
+        if no_pdl:
+            monkeypatch.setenv('D3D_NO_PDL', no_pdl)
+        else:
+            monkeypatch.delenv('D3D_NO_PDL', raising=False)
+        ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, seed=23)
+        ctx.set_params(init[None])
+        ctx.forward(write_err=True)
+        chain = np.zeros((1, 4, H, W, 3))
+        lik = np.zeros((1, 4, H, W))
+        acc, its, _ = ctx.sweep(1, 3, mode=nat.COLOURED, keep_one_in=1, min_acceptance_rate=0.0,
+                                chain_out=chain, lik_out=lik)
+        assert ctx.last_kernel() == 'sweep_colour_cluster_kernel'
+        out.append((chain, lik, ctx.get_residual().copy(), acc.copy(), its.copy()))
+        ctx.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert out[0][3][0] > 0                                       # something was accepted
