@@ -366,19 +366,30 @@ apply_records_cluster_kernel(const __grid_constant__ Problem pb, const double* r
     const int W = pb.W, H = pb.H, Dp = pb.Dp;
     const int y = site / W, x = site - y * W;
     if (y >= pb.ty0 && y < pb.ty1 && x >= pb.tx0 && x < pb.tx1) return;      // mine
-    Smem sm;
-    carve(sm, smem_raw, pb);
-    load_constants(sm, pb);
     const size_t HW = (size_t)H * W;
     double* prm = pb.params + ((size_t)chain * HW + site) * 3;
-    const double a_o = prm[0], c_o = prm[1], w_o = prm[2];
     const double a_n = r[REC_A], c_n = r[REC_C], w_n = r[REC_W];
-    __syncthreads();
-    cluster.sync();                                        // every CTA has read the old parameters
     const int y0 = max(max(y - pb.fhh, 0), pb.ry0), y1 = min(min(y + pb.fhh + 1, H), pb.ry1);
     const int x0 = max(max(x - pb.fhw, 0), pb.rx0), x1 = min(min(x + pb.fhw + 1, W), pb.rx1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (y0 < y1 && x0 < x1) {
+    if (!(y0 < y1 && x0 < x1)) {
+        // window outside the region this context keeps valid: book-keeping only (whole cluster)
+        if (cr == 0 && tid == 0) {
+            prm[0] = a_n; prm[1] = c_n; prm[2] = w_n;
+            pb.lik_cur[(size_t)chain * HW + site] = r[REC_LIK];
+            const int acc = r[REC_ACC] != 0.0;
+            pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+            if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+        }
+        return;
+    }
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    load_constants(sm, pb);
+    const double a_o = prm[0], c_o = prm[1], w_o = prm[2];
+    __syncthreads();
+    cluster.sync();                                        // every CTA has read the old parameters
+    {
         if (warp == 0) warp_line_profile(pb, sm, c_o, w_o, sm.g_o, sm.Lu_o, lane);
         else if (warp == 1) warp_line_profile(pb, sm, c_n, w_n, sm.g_n, sm.Lu_n, lane);
         __syncthreads();
@@ -548,19 +559,32 @@ apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ Til
     const int chain = (int)r[REC_CHAIN];
     const int W = pb.W, H = pb.H, Dp = pb.Dp;
     const int y = site / W, x = site - y * W;
-    Smem sm;
-    carve(sm, smem_raw, pb);
-    load_constants(sm, pb);
     const size_t HW = (size_t)H * W;
     double* prm = pb.params + ((size_t)chain * HW + site) * 3;
-    const double a_o = prm[0], c_o = prm[1], w_o = prm[2];
     const double a_n = r[REC_A], c_n = r[REC_C], w_n = r[REC_W];
-    __syncthreads();
-    if (CLUSTER) cg::this_cluster().sync();                 // every CTA has read the old parameters
     const int y0 = max(max(y - pb.fhh, 0), pb.ry0), y1 = min(min(y + pb.fhh + 1, H), pb.ry1);
     const int x0 = max(max(x - pb.fhw, 0), pb.rx0), x1 = min(min(x + pb.fhw + 1, W), pb.rx1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (y0 < y1 && x0 < x1) {
+    if (!(y0 < y1 && x0 < x1)) {
+        // The window of this record misses the region this context keeps valid -- most records of a
+        // big field: only the book-keeping of the site, no constants, no profiles, no barrier (the
+        // test is the same for every CTA of the cluster).
+        if (cr == 0 && tid == 0) {
+            prm[0] = a_n; prm[1] = c_n; prm[2] = w_n;
+            pb.lik_cur[(size_t)chain * HW + site] = r[REC_LIK];
+            const int acc = r[REC_ACC] != 0.0;
+            pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+            if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+        }
+        return;
+    }
+    Smem sm;
+    carve(sm, smem_raw, pb);
+    load_constants(sm, pb);
+    const double a_o = prm[0], c_o = prm[1], w_o = prm[2];
+    __syncthreads();
+    if (CLUSTER) cg::this_cluster().sync();                 // every CTA has read the old parameters
+    {
         if (warp == 0) warp_line_profile(pb, sm, c_o, w_o, sm.g_o, sm.Lu_o, lane);
         else if (warp == 1) warp_line_profile(pb, sm, c_n, w_n, sm.g_n, sm.Lu_n, lane);
         __syncthreads();
