@@ -191,6 +191,8 @@ struct d3d_ctx {
     int* d_sites_colour = nullptr;      // [cube][max_sites] colour-class order
     // fused tile exchange (d3d_tile.cuh): this context's box and the peers' boxes
     void* box = nullptr; size_t box_bytes = 0; bool box_attr_set = false;
+    int* d_hits = nullptr; unsigned int* d_hit_count = nullptr;   // triage of the fused exchange (d3d_tile.cuh):
+    long long hits_stride = 0;                                    // records per phase that reach into this tile's region
     TileBox tb;
     std::vector<void*> ipc_opened;
     int cluster = 0;                    // > 1: generic colour kernels work a site with a CTA cluster
@@ -267,6 +269,8 @@ extern "C" int d3d_ctx_destroy(d3d_ctx* c) {
     if (c->d_rec_stage) dev_free(c->d_rec_stage);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->box) cudaFree(c->box);
+    if (c->d_hits) cudaFree(c->d_hits);
+    if (c->d_hit_count) cudaFree(c->d_hit_count);
     if (c->rt_x) dev_free(c->rt_x);
     if (c->rt_yu) dev_free(c->rt_yu);
     if (c->rt_nc) dev_free(c->rt_nc);
@@ -1781,6 +1785,15 @@ extern "C" int d3d_tile_fused_init(d3d_ctx* c, int n_tiles, int my_index, void**
         c->tb.timeout_cycles = (long long)(secs * 2.0e9);
     }
     CK(cudaMemset(c->pb.status, 0, sizeof(int)));            // a fresh exchange forgets an earlier time-out
+    {   // hit lists of the triage pass, one per phase parity.  Bound: lattice sites of one colour class
+        // whose window can reach into the region this context keeps valid.
+        const long long ny = (pb.ry1 - pb.ry0 + 2 * pb.fhh) / pb.fh + 2, nx = (pb.rx1 - pb.rx0 + 2 * pb.fhw) / pb.fw + 2;
+        c->hits_stride = std::min<long long>((long long)n_tiles * slots, (long long)pb.n_chains * ny * nx);
+        if (c->d_hits) { cudaFree(c->d_hits); c->d_hits = nullptr; }
+        if (!c->d_hit_count) CK(cudaMalloc(&c->d_hit_count, 2 * sizeof(unsigned int)));
+        CK(cudaMalloc(&c->d_hits, (size_t)2 * c->hits_stride * sizeof(int)));
+        CK(cudaMemset(c->d_hit_count, 0, 2 * sizeof(unsigned int)));
+    }
     if (box_out) *box_out = c->box;
     if (box_bytes) *box_bytes = (int64_t)bytes;
     return 0;
@@ -1852,8 +1865,22 @@ extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int
         cudaFuncSetAttribute(apply_box_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->sweep_smem);
         c->box_attr_set = true;
     }
-    const long long n_rec = (long long)c->tb.n_tiles * n;
+    long long n_rec = (long long)c->tb.n_tiles * n;
     const unsigned long long ph = (unsigned long long)phase_index;
+    // triage first (one thread per record: flag wait, book-keeping, list of the records that reach
+    // into this tile's region), then clusters only for that list; D3D_TILE_NO_TRIAGE=1: a cluster
+    // per slot of every tile as before
+    const int* hits = nullptr; const unsigned int* hit_count = nullptr;
+    const long long hit_bound = std::min<long long>(
+        n_rec, (long long)pb.n_chains * ((pb.ry1 - pb.ry0 + 2 * pb.fhh) / pb.fh + 2) * ((pb.rx1 - pb.rx0 + 2 * pb.fhw) / pb.fw + 2));
+    if (c->d_hits && hit_bound <= c->hits_stride && !getenv("D3D_TILE_NO_TRIAGE")) {   // (tile unchanged since the init)
+        triage_box_kernel<<<(unsigned)((n_rec + 127) / 128), 128, 0, c->stream>>>(
+            pb, c->tb, ph, c->d_hits, c->d_hit_count, c->hits_stride, (unsigned int)c->hits_stride);
+        c->launches++;
+        CK(cudaGetLastError());
+        hits = c->d_hits; hit_count = c->d_hit_count;
+        n_rec = c->hits_stride;
+    }
     if (c->cluster) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_rec * c->cluster));
@@ -1864,11 +1891,11 @@ extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = c->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (c->dtype == D3D_F64) CK(cudaLaunchKernelEx(&cfg, apply_box_kernel<double, true>, pb, c->tb, ph));
-        else CK(cudaLaunchKernelEx(&cfg, apply_box_kernel<float, true>, pb, c->tb, ph));
+        if (c->dtype == D3D_F64) CK(cudaLaunchKernelEx(&cfg, apply_box_kernel<double, true>, pb, c->tb, ph, hits, hit_count, c->hits_stride));
+        else CK(cudaLaunchKernelEx(&cfg, apply_box_kernel<float, true>, pb, c->tb, ph, hits, hit_count, c->hits_stride));
     } else {
-        if (c->dtype == D3D_F64) apply_box_kernel<double, false><<<(unsigned)n_rec, 256, c->sweep_smem, c->stream>>>(pb, c->tb, ph);
-        else apply_box_kernel<float, false><<<(unsigned)n_rec, 256, c->sweep_smem, c->stream>>>(pb, c->tb, ph);
+        if (c->dtype == D3D_F64) apply_box_kernel<double, false><<<(unsigned)n_rec, 256, c->sweep_smem, c->stream>>>(pb, c->tb, ph, hits, hit_count, c->hits_stride);
+        else apply_box_kernel<float, false><<<(unsigned)n_rec, 256, c->sweep_smem, c->stream>>>(pb, c->tb, ph, hits, hit_count, c->hits_stride);
         CK(cudaGetLastError());
     }
     c->launches++;

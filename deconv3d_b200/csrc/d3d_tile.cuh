@@ -519,9 +519,53 @@ __device__ __forceinline__ bool tile_wait_flag(const TileBox& tb, int src, unsig
 
 // Applier of the fused exchange: grid = n_tiles * slots clusters (or CTAs); record (src, slot) is
 // read from this context's own box once the source tile has published the phase.
+// Triage of the fused exchange: ONE THREAD per (source tile, slot) waits for the source's flag, reads
+// the record and does the book-keeping of the remote site (parameters, likelihood, accept flag and
+// count); the few records whose window reaches into the region this context keeps valid are appended
+// to hits[parity][..] for the cluster applier.  Without it the applier's grid is a cluster per slot
+// of every tile (10 000 CTAs at 1024 x 1024 on four GPUs), each of which waits for a flag and passes
+// two cluster barriers before all but a few dozen find nothing to do.  Records of one phase have
+// disjoint windows: the order of the list does not matter.
+__global__ void triage_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ TileBox tb,
+                                  unsigned long long phase, int* hits, unsigned int* hit_count,
+                                  long long hits_stride, unsigned int max_hits) {
+    const int par = (int)(phase & 1ull);
+    if (blockIdx.x == 0 && threadIdx.x == 0) hit_count[par ^ 1] = 0u;   // the next phase's counter
+    const long long ridx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ridx >= (long long)tb.n_tiles * tb.slots) return;
+    const int src = (int)(ridx / tb.slots);
+    if (src == tb.my_tile) return;
+    if (*(volatile int*)pb.status == 2 || !tile_wait_flag(tb, src, phase)) { atomicExch(pb.status, 2); return; }
+    const double* rp = tb.inbox[tb.my_tile] + tile_inbox_index(tb, par, src, ridx - (long long)src * tb.slots);
+    double r[REC_N];
+#pragma unroll
+    for (int k = 0; k < REC_N; ++k) r[k] = __ldcg(rp + k);
+    const int site = (int)r[REC_SITE];
+    if (site < 0) return;
+    const int chain = (int)r[REC_CHAIN];
+    const int W = pb.W, H = pb.H;
+    const int y = site / W, x = site - y * W;
+    const int y0 = max(max(y - pb.fhh, 0), pb.ry0), y1 = min(min(y + pb.fhh + 1, H), pb.ry1);
+    const int x0 = max(max(x - pb.fhw, 0), pb.rx0), x1 = min(min(x + pb.fhw + 1, W), pb.rx1);
+    if (y0 < y1 && x0 < x1) {                                // the applier does its book-keeping too
+        const unsigned int k = atomicAdd(hit_count + par, 1u);
+        if (k < max_hits) hits[(size_t)par * hits_stride + k] = (int)ridx;
+        else atomicExch(pb.status, 2);                       // (cannot happen: max_hits bounds the geometry)
+        return;
+    }
+    const size_t HW = (size_t)H * W;
+    double* prm = pb.params + ((size_t)chain * HW + site) * 3;
+    prm[0] = r[REC_A]; prm[1] = r[REC_C]; prm[2] = r[REC_W];
+    pb.lik_cur[(size_t)chain * HW + site] = r[REC_LIK];
+    const int acc = r[REC_ACC] != 0.0;
+    pb.acc_cur[(size_t)chain * HW + site] = (uint8_t)acc;
+    if (acc) atomicAdd((unsigned long long*)&pb.accepted[chain], 1ull);
+}
+
 template <typename T, bool CLUSTER>
 __global__ void __launch_bounds__(256)
-apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ TileBox tb, unsigned long long phase) {
+apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ TileBox tb, unsigned long long phase,
+                 const int* hits = nullptr, const unsigned int* hit_count = nullptr, long long hits_stride = 0) {
     typedef typename Vec<T>::V V;
     const int VEC = Vec<T>::N;
     int CS = 1, cr = 0;
@@ -530,9 +574,16 @@ apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ Til
         CS = (int)cluster.num_blocks(); cr = (int)cluster.block_rank();
     }
     extern __shared__ double smem_raw[];
-    const long long ridx = blockIdx.x / CS;
+    long long ridx = blockIdx.x / CS;
+    if (hits) {
+        // behind triage_box_kernel: cluster i takes entry i of this phase's list (flags already seen)
+        const int par = (int)(phase & 1ull);
+        if (ridx >= (long long)hit_count[par]) return;       // (whole cluster)
+        ridx = hits[(size_t)par * hits_stride + ridx];
+    }
     const int src = (int)(ridx / tb.slots);
     if (src == tb.my_tile) return;                           // (whole cluster)
+    if (!hits) {
     __shared__ int s_ok;
     // (after one time-out every later applier gives up at once: a dead peer costs seconds, not
     // seconds per phase).  In a cluster the LEADER alone decides and shares its verdict through
@@ -550,6 +601,7 @@ apply_box_kernel(const __grid_constant__ Problem pb, const __grid_constant__ Til
         ok = s_ok;
     }
     if (!ok) { if (threadIdx.x == 0) atomicExch(pb.status, 2); return; }
+    }
     const double* rp = tb.inbox[tb.my_tile] + tile_inbox_index(tb, (int)(phase & 1ull), src, ridx - (long long)src * tb.slots);
     double r[REC_N];
 #pragma unroll
