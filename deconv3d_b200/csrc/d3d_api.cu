@@ -1868,12 +1868,18 @@ extern "C" int d3d_colour_phase_fused(d3d_ctx* c, int64_t iteration, int cy, int
     long long n_rec = (long long)c->tb.n_tiles * n;
     const unsigned long long ph = (unsigned long long)phase_index;
     // triage first (one thread per record: flag wait, book-keeping, list of the records that reach
-    // into this tile's region), then clusters only for that list; D3D_TILE_NO_TRIAGE=1: a cluster
-    // per slot of every tile as before
+    // into this tile's region), then clusters only for that list; otherwise a cluster per slot of
+    // every tile
     const int* hits = nullptr; const unsigned int* hit_count = nullptr;
     const long long hit_bound = std::min<long long>(
         n_rec, (long long)pb.n_chains * ((pb.ry1 - pb.ry0 + 2 * pb.fhh) / pb.fh + 2) * ((pb.rx1 - pb.rx0 + 2 * pb.fhw) / pb.fw + 2));
-    if (c->d_hits && hit_bound <= c->hits_stride && !getenv("D3D_TILE_NO_TRIAGE")) {   // (tile unchanged since the init)
+    // Worth a fourth launch per phase once the cluster-per-slot grid is more than a few waves (the
+    // 256 x 256 cube on two GPUs -- 98 slots x 6 CTAs -- is faster without: 93 against 99 ms per sweep).
+    // D3D_TILE_TRIAGE=1 / 0 forces / forbids it.
+    bool triage = n_rec * std::max(c->cluster, 1) > 1024;
+    if (const char* e = getenv("D3D_TILE_TRIAGE")) triage = atoi(e) != 0;
+    if (getenv("D3D_TILE_NO_TRIAGE")) triage = false;
+    if (triage && c->d_hits && hit_bound <= c->hits_stride) {   // (tile unchanged since the init)
         triage_box_kernel<<<(unsigned)((n_rec + 127) / 128), 128, 0, c->stream>>>(
             pb, c->tb, ph, c->d_hits, c->d_hit_count, c->hits_stride, (unsigned int)c->hits_stride);
         c->launches++;

@@ -28,7 +28,10 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok = True
-    for fused in (False, True):
+    for fused in (False, True, 'triage'):
+      # fused exchange with both appliers: cluster per slot (D3D_TILE_TRIAGE=0) and triage + list (=1)
+      if fused:
+          os.environ['D3D_TILE_TRIAGE'] = '1' if fused == 'triage' else '0'
       for shape, fsf_shape, chains, n_it in (((16, 30, 34), (13, 13), 2, 3), ((64, 44, 50), (41, 41), 1, 2)):
         prob = _problem(shape[0], shape[1], shape[2], fsf_shape, 3)
         data, var, fsf, lsf, mask, init = prob
@@ -48,7 +51,7 @@ def main():
             return ctx
 
         ctx = make(local)
-        sw = d3dist.TiledSweeper([ctx], (H, W), fsf.shape, fused=fused)
+        sw = d3dist.TiledSweeper([ctx], (H, W), fsf.shape, fused=bool(fused))
         chain = np.zeros((chains, n_it + 1, H, W, 3))
         lik = np.zeros((chains, n_it + 1, H, W))
         acc, its = sw.sweep(1, n_it, refresh_every=0, chain_out=chain, lik_out=lik)
@@ -63,7 +66,7 @@ def main():
                     np.array_equal(lik[:, 1:][:, :, m], lik1[:, 1:][:, :, m]) and
                     np.array_equal(acc, acc1))
             print('tiled over %d GPUs (%s), field %dx%d fsf %dx%d: %s (exchanges %d)'
-                  % (world, 'fused P2P' if fused else 'NCCL all-gather', H, W, fsf_shape[0], fsf_shape[1],
+                  % (world, ('fused P2P + triage' if fused == 'triage' else 'fused P2P') if fused else 'NCCL all-gather', H, W, fsf_shape[0], fsf_shape[1],
                      'IDENTICAL' if same else 'DIFFERENT', sw.exchanges))
             ok = ok and same
         # every rank must hold the same complete chain

@@ -99,11 +99,15 @@ def test_tiling_large_fsf_generic_kernel(nat):
         np.testing.assert_allclose(r, res1, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize('triage', ['0', '1'])
 @pytest.mark.parametrize('case', ['rowsite-13x13', 'cluster-41x41'])
-def test_fused_peer_memory_exchange_equals_one_context(nat, case):
+def test_fused_peer_memory_exchange_equals_one_context(nat, monkeypatch, case, triage):
     """The records go straight into the other tiles' boxes and the appliers wait on flags: no
     collective, no host round trip per phase (here the tiles share one GPU, each on its own
-    stream; on a multi-GPU box the same stores travel over NVLink)."""
+    stream; on a multi-GPU box the same stores travel over NVLink).  Both appliers: a cluster (or
+    CTA) per slot of every tile, and the triage pass (one thread per record) ahead of clusters for
+    the records that reach into the tile's region -- the library picks by grid size, forced here."""
+    monkeypatch.setenv('D3D_TILE_TRIAGE', triage)
     if case == 'rowsite-13x13':
         prob, chains, n_it, n_tiles = _problem(16, 30, 34, (13, 13), 3), 2, 3, 3
     else:
@@ -119,12 +123,14 @@ def test_fused_peer_memory_exchange_equals_one_context(nat, case):
         np.testing.assert_allclose(r, res1, rtol=0, atol=1e-9)
 
 
-def test_fused_exchange_gives_up_on_a_silent_peer(nat, monkeypatch):
+@pytest.mark.parametrize('triage', ['0', '1'])
+def test_fused_exchange_gives_up_on_a_silent_peer(nat, monkeypatch, triage):
     """A peer that never publishes its phase must not hang the GPU: the applier's wait is bounded
     (D3D_TILE_TIMEOUT_S, 30 s by default; 2 s here), later phases give up at once, and the error
     surfaces through the C ABI."""
     import time
     monkeypatch.setenv('D3D_TILE_TIMEOUT_S', '2')
+    monkeypatch.setenv('D3D_TILE_TRIAGE', triage)
     prob = _problem(8, 12, 14, (5, 5), 2)
     data, var, fsf, lsf, mask, init = prob
     ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, mask=mask, seed=3)
