@@ -423,9 +423,12 @@ def main():
         e2e = run_e2e(args, wl, arrays, rank, local_rank, world, sweeps)
 
     # cfg4 strong-scaling probe: every rank takes part (the one path with an exchange step)
-    cfg4 = None
+    cfg4 = cfg4_big = None
     if args.workload == 'cfg2x256' and args.mode == 'sequential' and not args.no_probes:
         cfg4 = tiled_probe(args, rank, local_rank, world)
+        # the same path on a field where a colour phase is several waves of CTAs on one GPU: the
+        # size from which tiling over GPUs pays (749 ms per sweep on one B200, 326 on four, 252 on eight)
+        cfg4_big = tiled_probe(args, rank, local_rank, world, field=1024)
 
     if world > 1 and rank != 0:
         dist.destroy_process_group()
@@ -484,6 +487,8 @@ def main():
         line.update(e2e)                                  # e2e_keep1, e2e_chain_on_device
     if cfg4 is not None:
         line['cfg4_1gpu' if world == 1 else 'cfg4_tiled'] = cfg4
+    if cfg4_big is not None:
+        line['cfg4_1024_1gpu' if world == 1 else 'cfg4_1024_tiled'] = cfg4_big
     if world == 1 and args.workload == 'cfg2x256' and args.mode == 'sequential' and not args.no_probes:
         # every other BASELINE.json configuration as a sub-record (CUDA events, state resident)
         line['cfg2_single_chain'] = sweep_probe(args, local_rank, stream, 'cfg2', 1, 200, 50,
