@@ -1342,6 +1342,23 @@ static cudaError_t launch_colour_class(d3d_ctx* c, long long it, int cy, int cx,
         return cudaLaunchKernelEx(&cfg, sweep_colour_cluster_kernel<T, IV>, pb, it, cy, cx, nlx, chain_dev,
                                   lik_dev, rows_local, row_local);
     }
+    if (pdl) {                                   // behind another phase of the same sweep (see above)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(NE == 0 ? c->generic_threads : c->threads);
+        cfg.dynamicSmemBytes = c->sweep_smem;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        c->launches++;
+        if (NE == 0)
+            return cudaLaunchKernelEx(&cfg, sweep_colour_generic_kernel<T, IV>, pb, it, cy, cx, nlx, chain_dev,
+                                      lik_dev, rows_local, row_local);
+        return cudaLaunchKernelEx(&cfg, sweep_colour_kernel<T, IV, ne>, pb, it, cy, cx, nlx, chain_dev,
+                                  lik_dev, rows_local, row_local);
+    }
     if (NE == 0)
         sweep_colour_generic_kernel<T, IV><<<grid, c->generic_threads, c->sweep_smem, c->stream>>>(
             pb, it, cy, cx, nlx, chain_dev, lik_dev, rows_local, row_local);

@@ -1019,7 +1019,11 @@ __global__ void sweep_begin_kernel(const __grid_constant__ Problem pb, long long
     pb.iters[chain] = it + 1;
 }
 
+// (programmatic dependent launch between the colour phases of one sweep, launch_colour_class: the
+// next phase may be scheduled while this one drains; it sets up its constants and waits in front of
+// the site update, the first thing that reads what a neighbouring phase writes)
 #define D3D_COLOUR_PROLOGUE()                                                               \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");                         \
     extern __shared__ double smem_raw[];                                                    \
     Smem sm;                                                                                \
     carve(sm, smem_raw, pb);                                                                \
@@ -1034,6 +1038,7 @@ __global__ void sweep_begin_kernel(const __grid_constant__ Problem pb, long long
     if (pb.mask[(size_t)cube * pb.H * pb.W + site] != 1) return;                            \
     load_constants(sm, pb);                                                                 \
     __syncthreads();                                                                        \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                                      \
     const size_t HW = (size_t)pb.H * pb.W;                                                  \
     double* crow = crow_base                                                                \
         ? crow_base + (((size_t)chain * rows_local + row_local) * HW + site) * 3 : nullptr; \

@@ -829,3 +829,39 @@ def test_colour_phases_with_and_without_dependent_launch_agree(nat, monkeypatch,
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     assert out[0][3][0] > 0                                       # something was accepted
+
+
+@pytest.mark.parametrize('fs,chains', [(13, 1), (7, 5), (23, 2)])
+def test_row_mapped_colour_phases_with_and_without_dependent_launch_agree(nat, monkeypatch, fs, chains):
+    """Same check for the launch-per-class coloured mode on the row-mapped (7x7, 13x13) and generic
+    (23x23) window kernels: the phases of a sweep are programmatic dependents of each other there
+    too (D3D_COLOUR_PROLOGUE); identical chains, likelihood rows, residuals and counters."""
+    port, _, _ = _oracle()
+    rs = np.random.RandomState(fs)
+    D, H, W = 24, 30, 33
+    data = synthetic(D, H, W, 21)
+    fsf = port.moffat_fsf_image((fs, fs), 0.2, fwhm_arcsec=0.8, beta=2.5)
+    lsf = port.gaussian_lsf_vector(0.0002675, 1.25e-4, D)
+    var = 0.05 ** 2 * (1 + rs.rand(D, H, W))
+    init = np.dstack([rs.rand(H, W) * 4, 6 + rs.rand(H, W) * 12, 0.7 + rs.rand(H, W) * 2])
+    monkeypatch.setenv('D3D_COLOUR_BY_CHAIN', '0')                 # one launch per colour class
+    monkeypatch.setenv('D3D_CLUSTER', '0')
+    out = []
+    for no_pdl in (None, '1'):
+        if no_pdl:
+            monkeypatch.setenv('D3D_NO_PDL', no_pdl)
+        else:
+            monkeypatch.delenv('D3D_NO_PDL', raising=False)
+        ctx, _, _ = make_ctx(nat, data, var, fsf, lsf, chains=chains, seed=29)
+        ctx.set_params(np.broadcast_to(init, (chains, H, W, 3)).copy())
+        ctx.forward(write_err=True)
+        chain = np.zeros((chains, 5, H, W, 3))
+        lik = np.zeros((chains, 5, H, W))
+        acc, its, _ = ctx.sweep(1, 4, mode=nat.COLOURED, keep_one_in=1, min_acceptance_rate=0.0,
+                                chain_out=chain, lik_out=lik)
+        assert ctx.last_kernel() in ('sweep_colour_kernel', 'sweep_colour_generic_kernel')
+        out.append((chain, lik, ctx.get_residual().copy(), acc.copy(), its.copy()))
+        ctx.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert (out[0][3] > 0).all()
